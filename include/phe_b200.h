@@ -1,0 +1,141 @@
+/*
+ * phe_b200.h -- C ABI of the B200 (sm_100a) hand-evaluation / equity library.
+ *
+ * Drop-in boundary for the one data-parallel hot path of
+ * weipeilun/texasholdempocker-rl (paths below are relative to that tree):
+ *   evaluate_cards            env/game.py:10,675   (third-party phevaluator)
+ *   GameEnv.get_winner_set_v2 env/game.py:663-681
+ *   generate_game_result      env/game.py:551-558
+ *   simulate_processes        env/workflow.py:102-227 (equity plans, config/default.yml:73-133)
+ *   GameEnv.new_random        env/game.py:119-163  (uniform re-deal of hidden cards)
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every entry point returns 0 or a negative
+ *     PHE_E* status, never throws, never exits; phe_strerror() names a status.
+ *   - "device" entry points take DEVICE pointers owned by the caller and launch
+ *     asynchronously on `stream` (a cudaStream_t passed as void*, NULL = legacy
+ *     default stream) of the CURRENT device; nothing is synchronised or freed.
+ *   - "*_host" entry points take HOST pointers, stage through library-owned
+ *     pinned/device scratch, and return after the result is in the host buffer.
+ *   - the library owns only read-only lookup tables, built once per device.
+ *   - re-entrant; callable from many threads; CUDA is initialised lazily (safe
+ *     to load before fork()).
+ *
+ * Data formats
+ *   card id      : figure*4 + decor, figure 0 ('2') .. 12 ('A'), decor 0 C 1 D 2 H 3 S
+ *                  (utils/pokerhandevaluator_utils.py:3-4, env/constants.py:14-36).
+ *   card set     : uint64, bit 16*decor + figure  (four 16-bit suit lanes).
+ *   rank         : uint16, 1 (royal flush) .. 7462 (7-5-4-3-2 off-suit); LOWER wins
+ *                  (env/game.py:676-680).
+ *   equity state : two uint64 words {known, hero}: known = hero | revealed board
+ *                  (board size 0, 3, 4 or 5); hero = the two hole cards; bits 61-63
+ *                  of `hero` (bit 60 is the ace of spades) optionally hold a per-state
+ *                  opponent count 1..7 (0 = use the call's n_opp).
+ *   counts       : uint64[3] per state = {win, tie, loss}; tie = hero shares the
+ *                  minimum rank with at least one opponent (env/game.py:551-558).
+ */
+#ifndef PHE_B200_H
+#define PHE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHE_OK            0
+#define PHE_EINVAL       -1   /* bad argument (size, layout, null pointer) */
+#define PHE_ECUDA        -2   /* CUDA runtime error; see phe_last_cuda_error() */
+#define PHE_ENODEVICE    -3   /* no usable sm_100 device */
+#define PHE_EPLAN        -4   /* equity plan not expressible (see phe_equity_plan) */
+#define PHE_ENOMEM       -5
+
+#define PHE_LAYOUT_IDS    0   /* uint8[n][7] card ids */
+#define PHE_LAYOUT_MASKS  1   /* uint64[n] card sets  */
+
+#define PHE_NUM_RANKS     7462
+#define PHE_NUM_HANDS_7   133784560ull   /* C(52,7) */
+#define PHE_MAX_PLAYERS   9    /* hero + 8 opponents: 5 + 2*8 = 21 dealt cards at most */
+#define PHE_MAX_PLAN_STEPS 8
+
+const char *phe_strerror(int status);
+const char *phe_last_cuda_error(void);       /* thread-local text of the last PHE_ECUDA */
+int phe_version(void);
+
+/* Build (once) and upload the lookup tables for `device`, make it current. */
+int phe_init(int device);
+
+/* ---- evaluate_cards (env/game.py:675), batched ------------------------- */
+/* n seven-card hands -> n ranks.  Duplicate / out-of-range cards are the
+ * caller's error (checked in the Python layer, as phevaluator does). */
+int phe_eval7(const void *hands, int layout, int64_t n, uint16_t *ranks_out, void *stream);
+int phe_eval7_host(const void *hands, int layout, int64_t n, uint16_t *ranks_out);
+
+/* ---- exhaustive C(52,7) ------------------------------------------------- */
+/* Evaluates the 7-card combinations with colex index in [comb_begin, comb_end)
+ * (index = sum_i C(c_i, i+1) over sorted ids c_0 < ... < c_6) and ADDS to
+ * hist9[9] (SF, quads, full house, flush, straight, trips, two pair, pair,
+ * high card) and hist7463[7463] (bin = rank; bin 0 stays 0).  Either pointer
+ * may be NULL.  Shards of the index range may be summed in any order. */
+int phe_enum7(uint64_t *hist9, uint64_t *hist7463, uint64_t comb_begin, uint64_t comb_end, void *stream);
+int phe_enum7_host(uint64_t *hist9, uint64_t *hist7463, uint64_t comb_begin, uint64_t comb_end);
+
+/* ---- Monte-Carlo equity ------------------------------------------------- */
+/* For each state: deal the missing board cards and two cards to each of n_opp
+ * opponents, `rollouts` times, global sample indices sample_offset ..
+ * sample_offset+rollouts-1, and ADD {win, tie, loss} to wtl[3*state].  The deal
+ * is a pure function of (seed, state index, sample index): Philox4x32-10, key =
+ * seed, counter = (sample lo, sample hi, state_index_base + state, block);
+ * results do not depend on grid shape or on how samples are sharded. */
+int phe_equity_mc(const uint64_t *states, int64_t n_states, int n_opp, uint64_t rollouts,
+                  uint64_t sample_offset, uint64_t seed, uint32_t state_index_base,
+                  uint64_t *wtl, void *stream);
+int phe_equity_mc_host(const uint64_t *states, int64_t n_states, int n_opp, uint64_t rollouts,
+                       uint64_t sample_offset, uint64_t seed, uint32_t state_index_base,
+                       uint64_t *wtl);
+
+/* ---- exact-plan equity (simulate_processes, env/workflow.py:150-199) ---- */
+/* Heads-up.  exist[n_tasks][8]: the task's known cards as ids in deal order
+ * (hero 2, then flop 3, turn 1, river 1 as far as revealed), n_exist of them
+ * valid (2, 5, 6 or 7; same for the whole call).  plan[n_steps][3] (HOST
+ * pointer) = (gen_num, num_random, is_segment_end) rows of
+ * simulation_recurrent_params; every step but the last must have gen_num 1,
+ * and n_exist + sum(gen_num) must be 9, else PHE_EPLAN.  ADDS {win, tie, loss}
+ * to wtl[3*task]; num_estimation = win+tie+loss, game_result_sum = win - loss.
+ * The random step draws from the Philox stream with stream id
+ * stream_base + task and sample index leaf*num_random + draw. */
+int phe_equity_plan(const uint8_t *exist, int n_exist, int64_t n_tasks, const int32_t *plan,
+                    int n_steps, uint64_t seed, uint32_t stream_base, uint64_t *wtl, void *stream);
+int phe_equity_plan_host(const uint8_t *exist, int n_exist, int64_t n_tasks, const int32_t *plan,
+                         int n_steps, uint64_t seed, uint32_t stream_base, uint64_t *wtl);
+/* number of deals the plan generates for n_exist known cards (0 if invalid) */
+uint64_t phe_plan_num_deals(int n_exist, const int32_t *plan, int n_steps);
+
+/* ---- showdown (get_winner_set_v2, env/game.py:663-681) ------------------ */
+/* boards[n_games] (5-card sets), holes[n_games][n_players] (2-card sets),
+ * live[n_games] = bit p set if player p takes part.  winners_out[g] = bitmask
+ * of the live players holding the minimum rank; a game with one live player
+ * returns that player without evaluation (env/game.py:664-665).  ranks_out
+ * (optional) [n_games][n_players], 0 for players not evaluated. */
+int phe_showdown(const uint64_t *boards, const uint64_t *holes, const uint32_t *live,
+                 int64_t n_games, int n_players, uint32_t *winners_out, uint16_t *ranks_out, void *stream);
+int phe_showdown_host(const uint64_t *boards, const uint64_t *holes, const uint32_t *live,
+                      int64_t n_games, int n_players, uint32_t *winners_out, uint16_t *ranks_out);
+
+/* ---- determinisation (GameEnv.new_random, env/game.py:119-163) ---------- */
+/* For each of n deals: draw `need` (1..21) distinct cards uniformly from the cards not
+ * in known[i] (same Philox stream as phe_equity_mc: stream id
+ * stream_base + i, sample index sample_offset) and write their ids to
+ * cards_out[i*need ..]. */
+int phe_deal(const uint64_t *known, int64_t n, int need, uint64_t seed, uint64_t sample_offset,
+             uint32_t stream_base, uint8_t *cards_out, void *stream);
+int phe_deal_host(const uint64_t *known, int64_t n, int need, uint64_t seed, uint64_t sample_offset,
+                  uint32_t stream_base, uint8_t *cards_out);
+
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+uint64_t phe_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHE_B200_H */

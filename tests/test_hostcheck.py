@@ -1,0 +1,106 @@
+"""The arithmetic the sm_100a kernels execute (csrc/phe_core.cuh, table builder csrc/phe_tables.cpp),
+instantiated on the host by the test-only libphe_hostcheck.so and compared bit-exactly with the oracle.
+Covers every table entry, so a GPU/CPU difference can only come from the launch plumbing."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+def vp(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def test_table_image_every_entry(hostcheck, oracle):
+    img = np.zeros(81920, dtype=np.uint16)
+    hp = np.zeros(4, dtype=np.uint32)
+    hostcheck.hc_get_image(vp(img), vp(hp))
+    suits, flush, dp, noflush = oracle.tables()
+    assert (img[73728:] == flush).all()                      # all 8192 flush lanes
+    assert int((img[:65536] > 0).sum()) == 49205 == hostcheck.hc_num_keys()
+    assert sorted(img[:65536][img[:65536] > 0].tolist()) == sorted(noflush.tolist())   # same multiset of ranks
+
+
+def test_every_rank_multiset(hostcheck, oracle):
+    # one representative hand per non-flush rank multiset (49205) and per flush lane (4719)
+    hands = []
+
+    def rec(q, pos, left):
+        if pos == 13:
+            if left == 0:
+                c, n = [], 0
+                for r in range(13):
+                    for _ in range(q[r]):
+                        c.append(r * 4 + (n & 3)); n += 1
+                hands.append(c)
+            return
+        for d in range(min(4, left) + 1):
+            q[pos] = d
+            rec(q, pos + 1, left - d)
+        q[pos] = 0
+    rec([0] * 13, 0, 7)
+    for m in range(8192):
+        pc = bin(m).count("1")
+        if 5 <= pc <= 7:
+            c = [r * 4 + 3 for r in range(13) if m >> r & 1]
+            for r in range(13):
+                if len(c) < 7 and not (m >> r & 1):
+                    c.append(r * 4 + (len(c) & 1))
+            hands.append(c)
+    ids = np.array(hands, dtype=np.uint8)
+    masks = oracle.masks_from_ids(ids)
+    out = np.zeros(len(masks), dtype=np.uint16)
+    hostcheck.hc_eval7_masks(vp(masks), len(masks), vp(out))
+    assert (out == oracle.rank7_batch(ids)).all()
+    assert (out == oracle.rank7_batch(ids, brute=True)).all()
+
+
+def test_random_hands(hostcheck, oracle):
+    rng = np.random.default_rng(5)
+    ids = np.argsort(rng.random((500000, 52)), axis=1)[:, :7].astype(np.uint8)
+    masks = oracle.masks_from_ids(ids)
+    out = np.zeros(len(masks), dtype=np.uint16)
+    hostcheck.hc_eval7_masks(vp(masks), len(masks), vp(out))
+    assert (out == oracle.rank7_batch(ids)).all()
+
+
+def test_deal_stream(hostcheck, oracle):
+    rng = np.random.default_rng(6)
+    for i in range(500):
+        k = int(rng.integers(0, 8))
+        known = oracle.mask_of(rng.permutation(52)[:k])
+        need = int(rng.integers(1, 22))
+        got = np.zeros(need, dtype=np.uint8)
+        hostcheck.hc_deal(known, 1000 + i, i * 977, i, need, vp(got))
+        assert (got == oracle.deal(known, 1000 + i, i * 977, i, need)).all()
+
+
+@pytest.mark.parametrize("text,n_opp", [("As Ah", 1), ("As Ah 2c 7d Tc", 5), ("7h 8h 9h Th 2c 2d", 3),
+                                        ("Kd Kc 2c 7d Tc 3h 9s", 5), ("2c 7d", 8)])
+def test_mc_rollouts(hostcheck, oracle, text, n_opp):
+    ids = oracle.ids(text)
+    hero, known = oracle.mask_of(ids[:2]), oracle.mask_of(ids)
+    w = np.zeros(3, dtype=np.uint64)
+    hostcheck.hc_equity_mc(known, hero, n_opp, 5000, 123, 99, 3, vp(w))
+    assert (w.astype(np.int64) == oracle.equity_mc(known, hero, n_opp, 5000, 99, sample_offset=123, state_idx=3)).all()
+
+
+def test_colex_unrank(hostcheck, oracle):
+    rng = np.random.default_rng(7)
+    for idx in [0, 1, 2, 133784559, 77777777] + rng.integers(0, 133784560, 300).tolist():
+        c = np.zeros(7, dtype=np.int32)
+        hostcheck.hc_colex_unrank7(int(idx), vp(c))
+        assert (c == oracle.colex_unrank7(int(idx))).all()
+
+
+@pytest.mark.parametrize("text,rnd", [("As Ah 2c 7d Tc 3h 9s", 3), ("As Ah 2c 7d Tc 3h", 2), ("As Ah 2c 7d Tc", 1),
+                                      ("As Ah", 0), ("2c 3c", 0), ("Ks 2d 3c 4c 5c", 1), ("Kh Ks Ah Kd Kc 2c", 2)])
+def test_plans(hostcheck, oracle, text, rnd):
+    for plans in (oracle.DEFAULT_PLANS, oracle.DEBUG_PLANS):
+        plan = plans[rnd][0]
+        e = np.array(oracle.ids(text), dtype=np.uint8)
+        p = np.array([[a, b, int(c)] for a, b, c in plan], dtype=np.int32)
+        out = np.zeros(4, dtype=np.uint64)
+        assert hostcheck.hc_equity_plan(vp(e), len(e), vp(p), len(p), 5, 2, vp(out)) == 0
+        assert tuple(int(x) for x in out) == oracle.equity_plan(oracle.ids(text), plan, seed=5, stream=2)
+        assert int(out[3]) == plans[rnd][1] == hostcheck.hc_plan_num_deals(len(e), vp(p), len(p))

@@ -1,0 +1,60 @@
+"""Builds the sm_100a library (and the test-only host-check library) in-tree with nvcc / g++.
+
+Outputs land in texasholdempocker-rl_b200/lib/ (git-ignored, shipped to the GPU box by gpurun).
+"""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libphe_b200.so")
+HOSTCHECK = os.path.join(LIBDIR, "libphe_hostcheck.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-Wall", "--shared", "-cudart", "static",
+]
+
+
+def _sources(names):
+    return [os.path.join(CSRC, n) for n in names]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _all_deps():
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps.append(os.path.join(HERE, "..", "include", "phe_b200.h"))
+    return deps
+
+
+def nvcc_path():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def build_library(force=False, verbose=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    if force or _stale(LIB, _all_deps()):
+        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + _sources(["phe_kernels.cu", "phe_tables.cpp"])
+        subprocess.check_call(cmd)
+    return LIB
+
+
+def build_hostcheck(force=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    if force or _stale(HOSTCHECK, _all_deps()):
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-x", "c++"] + _sources(["phe_hostcheck.cpp", "phe_tables.cpp"]) + ["-o", HOSTCHECK]
+        subprocess.check_call(cmd)
+    return HOSTCHECK
+
+
+if __name__ == "__main__":
+    print(build_library(force=True, verbose=True))
+    print(build_hostcheck(force=True))

@@ -1,0 +1,103 @@
+// phe_hostcheck.cpp -- TEST-ONLY host instantiation of the device arithmetic in phe_core.cuh.
+//
+// Built into libphe_hostcheck.so and loaded only by tests/ (CPU, "not gpu"): it lets the exact
+// evaluator / dealing / unranking code the sm_100a kernels execute be compared with the oracle in
+// a container without a GPU.  It is not linked into libphe_b200.so and is not a CPU fallback:
+// the product library has no host compute path.
+#include <cstring>
+#include <vector>
+
+#include "phe_core.cuh"
+#include "phe_plan.h"
+#include "phe_tables.h"
+
+using namespace phe;
+
+static std::vector<uint16_t> g_image;
+static HashParams g_hp;
+static uint32_t g_binom[53 * 8];
+
+extern "C" {
+
+int hc_init(void)
+{
+    if (!g_image.empty()) return 0;
+    g_image.resize(TAB_U16);
+    if (!build_table_image(g_image.data(), &g_hp)) { g_image.clear(); return -1; }
+    build_binom(g_binom);
+    return 0;
+}
+
+void hc_get_image(uint16_t* out, uint32_t* hp4)
+{
+    std::memcpy(out, g_image.data(), TAB_BYTES);
+    hp4[0] = g_hp.a1; hp4[1] = g_hp.b1; hp4[2] = g_hp.a2; hp4[3] = g_hp.b2;
+}
+
+int hc_num_keys(void) { return (int)all_noflush_keys().size(); }
+
+void hc_eval7_masks(const uint64_t* m, int64_t n, uint16_t* out)
+{
+    GlobalTab tab{g_image.data()};
+    for (int64_t i = 0; i < n; i++) out[i] = (uint16_t)eval7(m[i], tab, g_hp);
+}
+
+void hc_deal(uint64_t known, uint64_t seed, uint64_t sample, uint32_t stream, int need, uint8_t* ids)
+{
+    const Dealt d = deal_cards(known, seed, sample, stream, need);
+    for (int i = 0; i < need; i++) ids[i] = (uint8_t)pos_to_id(d.get(i, need));
+}
+
+void hc_equity_mc(uint64_t known, uint64_t hero, int n_opp, uint64_t rollouts, uint64_t offset, uint64_t seed,
+                  uint32_t stream, uint64_t wtl[3])
+{
+    GlobalTab tab{g_image.data()};
+    const int nboard = __builtin_popcountll(known & ~hero);
+    for (uint64_t s = 0; s < rollouts; s++) wtl[mc_rollout(tab, g_hp, known, hero, nboard, n_opp, seed, offset + s, stream)]++;
+}
+
+void hc_colex_unrank7(uint64_t idx, int32_t* c)
+{
+    Binom C{g_binom};
+    int cc[7];
+    colex_unrank7(idx, C, cc);
+    for (int i = 0; i < 7; i++) c[i] = cc[i];
+}
+
+int hc_equity_plan(const uint8_t* exist, int n_exist, const int32_t* plan, int n_steps, uint64_t seed, uint32_t stream,
+                   uint64_t out[4])
+{
+    PlanDesc pd;
+    if (!parse_plan(n_exist, plan, n_steps, &pd)) return -4;
+    GlobalTab tab{g_image.data()};
+    Binom C{g_binom};
+    uint64_t known = 0;
+    for (int i = 0; i < n_exist; i++) known |= id_bit(exist[i]);
+    out[0] = out[1] = out[2] = out[3] = 0;
+    for (uint64_t leaf = 0; leaf < pd.n_leaves; leaf++) {
+        uint8_t cards[9];
+        std::memcpy(cards, exist, n_exist);
+        plan_unrank_leaf(pd, leaf, C, cards);
+        const int base = pd.n_exist + pd.n_enum;
+        if (pd.rnd_k == 0) {
+            out[plan_leaf_result(tab, g_hp, cards)]++; out[3]++;
+        } else {
+            uint64_t kn = known;
+            for (int i = pd.n_exist; i < base; i++) kn |= id_bit(cards[i]);
+            for (int j = 0; j < pd.rnd_n; j++) {
+                const Dealt d = deal_cards(kn, seed, leaf * (uint64_t)pd.rnd_n + (uint64_t)j, stream, pd.rnd_k);
+                for (int i = 0; i < pd.rnd_k; i++) cards[base + i] = (uint8_t)pos_to_id(d.get(i, pd.rnd_k));
+                out[plan_leaf_result(tab, g_hp, cards)]++; out[3]++;
+            }
+        }
+    }
+    return 0;
+}
+
+uint64_t hc_plan_num_deals(int n_exist, const int32_t* plan, int n_steps)
+{
+    PlanDesc pd;
+    return parse_plan(n_exist, plan, n_steps, &pd) ? plan_num_deals(pd) : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,806 @@
+// phe_kernels.cu -- sm_100a kernels and the C ABI declared in include/phe_b200.h.
+//
+// All kernels are integer / shared-memory-lookup work (no tensor cores): card sets are 64-bit
+// words, the 160 KB rank-table image is staged into shared memory once per CTA with a TMA bulk
+// copy (cp.async.bulk + mbarrier), grids are persistent (one 1024-thread CTA per SM), counts are
+// reduced with redux/shuffles before any atomic.  There is no host compute path: every entry
+// point either launches a kernel or returns an error.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/phe_b200.h"
+#include "phe_core.cuh"
+#include "phe_plan.h"
+#include "phe_tables.h"
+
+using namespace phe;
+
+// ------------------------------------------------------------------------------------------------
+// device-side constants
+// ------------------------------------------------------------------------------------------------
+__constant__ HashParams c_hp;
+__constant__ uint32_t c_binom[53 * 8];
+
+static constexpr int kCtaThreads = 1024;
+static constexpr int kHistBins = PHE_NUM_RANKS + 1;                 // 7463, bin = rank
+static constexpr int kHistBinsPad = 7464;
+static constexpr uint32_t kSmemTab = TAB_BYTES;                       // 163,840
+static constexpr uint32_t kSmemEnum = kSmemTab + kHistBinsPad * 4 + 9 * 8 + 16;
+static constexpr uint32_t kSmemTabOnly = kSmemTab + 16;
+
+// ------------------------------------------------------------------------------------------------
+// table staging: one TMA bulk copy of the whole image, completion on an mbarrier
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_tables(unsigned char* s_tab, const uint16_t* __restrict__ g_tab, uint64_t* s_bar)
+{
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_bar);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_tab);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TAB_BYTES) : "memory");
+        constexpr uint32_t kChunk = 32768;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(g_tab);
+#pragma unroll 1
+        for (uint32_t off = 0; off < TAB_BYTES; off += kChunk) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
+                         "l"(src + off), "r"(kChunk), "r"(bar)
+                         : "memory");
+        }
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(0u)
+            : "memory");
+    }
+}
+
+__device__ __forceinline__ uint64_t ld_nc_u64(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ uint64_t hand_from_ids(const uint8_t* p)
+{
+    uint64_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 7; i++) m |= id_bit(__ldg(p + i));
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: batched eval7 (evaluate_cards, env/game.py:675)
+// ------------------------------------------------------------------------------------------------
+template <int LAYOUT>
+__global__ void __launch_bounds__(kCtaThreads, 1)
+k_eval7_smem(const uint16_t* __restrict__ g_tab, const void* __restrict__ hands, int64_t n, uint16_t* __restrict__ out)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    stage_tables(smem, g_tab, reinterpret_cast<uint64_t*>(smem + kSmemTab));
+    const SharedTab tab{(uint32_t)__cvta_generic_to_shared(smem)};
+    const HashParams hp = c_hp;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (LAYOUT == PHE_LAYOUT_MASKS) {
+        const uint64_t* h = static_cast<const uint64_t*>(hands);
+        const bool vec = ((reinterpret_cast<uintptr_t>(h) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+        const int64_t n4 = vec ? (n >> 2) : 0;
+        // four hands per thread per trip: two 128-bit loads, one 64-bit store
+        for (int64_t q = gtid; q < n4; q += nthr) {
+            const ulonglong2 v0 = __ldcs(reinterpret_cast<const ulonglong2*>(h) + 2 * q);
+            const ulonglong2 v1 = __ldcs(reinterpret_cast<const ulonglong2*>(h) + 2 * q + 1);
+            const uint32_t r0 = eval7(v0.x, tab, hp), r1 = eval7(v0.y, tab, hp);
+            const uint32_t r2 = eval7(v1.x, tab, hp), r3 = eval7(v1.y, tab, hp);
+            uint2 o;
+            o.x = r0 | (r1 << 16);
+            o.y = r2 | (r3 << 16);
+            __stcs(reinterpret_cast<uint2*>(out) + q, o);
+        }
+        for (int64_t i = n4 * 4 + gtid; i < n; i += nthr) out[i] = (uint16_t)eval7(ld_nc_u64(h + i), tab, hp);
+    } else {
+        const uint8_t* h = static_cast<const uint8_t*>(hands);
+        for (int64_t i = gtid; i < n; i += nthr) out[i] = (uint16_t)eval7(hand_from_ids(h + 7 * i), tab, hp);
+    }
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256)
+k_eval7_gmem(const uint16_t* __restrict__ g_tab, const void* __restrict__ hands, int64_t n, uint16_t* __restrict__ out)
+{
+    const GlobalTab tab{g_tab};
+    const HashParams hp = c_hp;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t m = LAYOUT == PHE_LAYOUT_MASKS ? static_cast<const uint64_t*>(hands)[i]
+                                                  : hand_from_ids(static_cast<const uint8_t*>(hands) + 7 * i);
+    out[i] = (uint16_t)eval7(m, tab, hp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: exhaustive C(52,7) over a colex index range
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCtaThreads, 1)
+k_enum7(const uint16_t* __restrict__ g_tab, unsigned long long* __restrict__ hist9, unsigned long long* __restrict__ hist7463,
+        uint64_t begin, uint64_t end)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + kSmemTab);
+    unsigned long long* s_h9 = reinterpret_cast<unsigned long long*>(smem + kSmemTab + kHistBinsPad * 4);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_h9 + 9);
+    for (int i = threadIdx.x; i < kHistBinsPad; i += blockDim.x) s_hist[i] = 0;
+    if (threadIdx.x < 9) s_h9[threadIdx.x] = 0;
+    stage_tables(smem, g_tab, s_bar);   // contains a __syncthreads after the zeroing stores
+    __syncthreads();
+    const SharedTab tab{(uint32_t)__cvta_generic_to_shared(smem)};
+    const HashParams hp = c_hp;
+
+    const uint64_t total = end - begin;
+    const uint64_t nthr = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t per = (total + nthr - 1) / nthr;
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t my_b = begin + gtid * per;
+    uint64_t my_e = my_b + per;
+    if (my_e > end) my_e = end;
+    if (my_b < my_e) {
+        int c[7];
+        colex_unrank7(my_b, Binom{c_binom}, c);
+        int c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4], c5 = c[5], c6 = c[6];
+        uint64_t s2 = id_bit(c2) | id_bit(c3) | id_bit(c4) | id_bit(c5) | id_bit(c6);
+        uint64_t s1 = s2 | id_bit(c1);
+        const uint32_t n = (uint32_t)(my_e - my_b);
+#pragma unroll 1
+        for (uint32_t it = 0; it < n; ++it) {
+            const uint32_t r = eval7(s1 | id_bit(c0), tab, hp);
+            atomicAdd(&s_hist[r], 1u);
+            // colex successor: smallest element runs fastest
+            ++c0;
+            if (c0 == c1) {
+                c0 = 0; ++c1;
+                if (c1 == c2) {
+                    c1 = 1; ++c2;
+                    if (c2 == c3) {
+                        c2 = 2; ++c3;
+                        if (c3 == c4) {
+                            c3 = 3; ++c4;
+                            if (c4 == c5) {
+                                c4 = 4; ++c5;
+                                if (c5 == c6) { c5 = 5; ++c6; }
+                            }
+                        }
+                    }
+                    s2 = id_bit(c2) | id_bit(c3) | id_bit(c4) | id_bit(c5) | id_bit(c6);
+                }
+                s1 = s2 | id_bit(c1);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHistBins; i += blockDim.x) {
+        const uint32_t v = s_hist[i];
+        if (v) {
+            if (hist7463) atomicAdd(hist7463 + i, (unsigned long long)v);
+            if (hist9) atomicAdd(s_h9 + category_of(i), (unsigned long long)v);
+        }
+    }
+    __syncthreads();
+    if (hist9 && threadIdx.x < 9 && s_h9[threadIdx.x]) atomicAdd(hist9 + threadIdx.x, s_h9[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: Monte-Carlo equity.  One warp works on one (state, sample chunk) item at a time; lanes take
+// samples chunk_begin + lane + 32 i.  The deal is a pure function of the global sample index.
+// ------------------------------------------------------------------------------------------------
+template <class Tab>
+__device__ __forceinline__ void equity_mc_body(const Tab& tab, const ulonglong2* __restrict__ states, int64_t n_states,
+                                               int n_opp_default, uint64_t rollouts, uint64_t sample_offset, uint64_t seed,
+                                               uint32_t state_base, unsigned long long* __restrict__ wtl, uint32_t chunk)
+{
+    const HashParams hp = c_hp;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warps_per_cta = blockDim.x >> 5;
+    const uint64_t nwarps = (uint64_t)gridDim.x * warps_per_cta;
+    const uint64_t chunks_per_state = (rollouts + chunk - 1) / chunk;
+    const uint64_t items = (uint64_t)n_states * chunks_per_state;
+    for (uint64_t item = (uint64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); item < items; item += nwarps) {
+        const uint64_t s = item / chunks_per_state, ch = item - s * chunks_per_state;
+        const ulonglong2 st = states[s];
+        const uint64_t known = st.x & CARD_BITS, hero = st.y & CARD_BITS;
+        const int over = (int)(st.y >> 61);
+        const int n_opp = over ? over : n_opp_default;
+        const int nboard = __popcll(known & ~hero);
+        const uint64_t b = ch * chunk;
+        uint64_t e = b + chunk;
+        if (e > rollouts) e = rollouts;
+        uint32_t w = 0, t = 0, l = 0;
+        for (uint64_t i = b + lane; i < e; i += 32) {
+            const int res = mc_rollout(tab, hp, known, hero, nboard, n_opp, seed, sample_offset + i, state_base + (uint32_t)s);
+            w += (res == 0); t += (res == 1); l += (res == 2);
+        }
+        w = __reduce_add_sync(0xFFFFFFFFu, w);
+        t = __reduce_add_sync(0xFFFFFFFFu, t);
+        l = __reduce_add_sync(0xFFFFFFFFu, l);
+        if (lane == 0) {
+            if (w) atomicAdd(wtl + 3 * s + 0, (unsigned long long)w);
+            if (t) atomicAdd(wtl + 3 * s + 1, (unsigned long long)t);
+            if (l) atomicAdd(wtl + 3 * s + 2, (unsigned long long)l);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kCtaThreads, 1)
+k_equity_mc_smem(const uint16_t* __restrict__ g_tab, const ulonglong2* __restrict__ states, int64_t n_states, int n_opp,
+                 uint64_t rollouts, uint64_t sample_offset, uint64_t seed, uint32_t state_base,
+                 unsigned long long* __restrict__ wtl, uint32_t chunk)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    stage_tables(smem, g_tab, reinterpret_cast<uint64_t*>(smem + kSmemTab));
+    const SharedTab tab{(uint32_t)__cvta_generic_to_shared(smem)};
+    equity_mc_body(tab, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk);
+}
+
+__global__ void __launch_bounds__(256)
+k_equity_mc_gmem(const uint16_t* __restrict__ g_tab, const ulonglong2* __restrict__ states, int64_t n_states, int n_opp,
+                 uint64_t rollouts, uint64_t sample_offset, uint64_t seed, uint32_t state_base,
+                 unsigned long long* __restrict__ wtl, uint32_t chunk)
+{
+    const GlobalTab tab{g_tab};
+    equity_mc_body(tab, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3b: exact-plan equity (simulate_processes).  One thread per enumeration leaf.
+// ------------------------------------------------------------------------------------------------
+template <class Tab>
+__device__ __forceinline__ void equity_plan_body(const Tab& tab, const uint8_t* __restrict__ exist, int64_t n_tasks,
+                                                 const PlanDesc& pd, uint64_t seed, uint32_t stream_base,
+                                                 unsigned long long* __restrict__ wtl)
+{
+    const HashParams hp = c_hp;
+    const Binom C{c_binom};
+    const uint64_t total = (uint64_t)n_tasks * pd.n_leaves;
+    const uint64_t nthr = (uint64_t)gridDim.x * blockDim.x;
+    const int base = pd.n_exist + pd.n_enum;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthr) {
+        const uint64_t task = idx / pd.n_leaves, leaf = idx - task * pd.n_leaves;
+        uint8_t cards[9];
+        uint64_t known = 0;
+        for (int i = 0; i < pd.n_exist; i++) {
+            cards[i] = __ldg(exist + task * 8 + i);
+            known |= id_bit(cards[i]);
+        }
+        plan_unrank_leaf(pd, leaf, C, cards);
+        uint32_t w = 0, t = 0, l = 0;
+        if (pd.rnd_k == 0) {
+            const int res = plan_leaf_result(tab, hp, cards);
+            w = (res == 0); t = (res == 1); l = (res == 2);
+        } else {
+            for (int i = pd.n_exist; i < base; i++) known |= id_bit(cards[i]);
+            for (int j = 0; j < pd.rnd_n; j++) {
+                const Dealt d = deal_cards(known, seed, leaf * (uint64_t)pd.rnd_n + (uint64_t)j, stream_base + (uint32_t)task, pd.rnd_k);
+                for (int i = 0; i < pd.rnd_k; i++) cards[base + i] = (uint8_t)pos_to_id(d.get(i, pd.rnd_k));
+                const int res = plan_leaf_result(tab, hp, cards);
+                w += (res == 0); t += (res == 1); l += (res == 2);
+            }
+        }
+        // aggregate lanes that work on the same task before touching global memory
+        const unsigned act = __activemask();
+        const unsigned same = __match_any_sync(act, (unsigned long long)task);
+        const int leader = __ffs(same) - 1;
+        for (int off = 16; off > 0; off >>= 1) {
+            const uint32_t w2 = __shfl_down_sync(act, w, off), t2 = __shfl_down_sync(act, t, off), l2 = __shfl_down_sync(act, l, off);
+            const int src = (threadIdx.x & 31) + off;
+            if (src < 32 && (same >> src & 1)) { w += w2; t += t2; l += l2; }
+        }
+        if ((int)(threadIdx.x & 31) == leader) {
+            if (w) atomicAdd(wtl + 3 * task + 0, (unsigned long long)w);
+            if (t) atomicAdd(wtl + 3 * task + 1, (unsigned long long)t);
+            if (l) atomicAdd(wtl + 3 * task + 2, (unsigned long long)l);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kCtaThreads, 1)
+k_equity_plan_smem(const uint16_t* __restrict__ g_tab, const uint8_t* __restrict__ exist, int64_t n_tasks, PlanDesc pd, uint64_t seed,
+                   uint32_t stream_base, unsigned long long* __restrict__ wtl)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    stage_tables(smem, g_tab, reinterpret_cast<uint64_t*>(smem + kSmemTab));
+    const SharedTab tab{(uint32_t)__cvta_generic_to_shared(smem)};
+    equity_plan_body(tab, exist, n_tasks, pd, seed, stream_base, wtl);
+}
+
+__global__ void __launch_bounds__(256)
+k_equity_plan_gmem(const uint16_t* __restrict__ g_tab, const uint8_t* __restrict__ exist, int64_t n_tasks, PlanDesc pd, uint64_t seed,
+                   uint32_t stream_base, unsigned long long* __restrict__ wtl)
+{
+    const GlobalTab tab{g_tab};
+    equity_plan_body(tab, exist, n_tasks, pd, seed, stream_base, wtl);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: showdown (get_winner_set_v2, env/game.py:663-681).  One thread per game.
+// ------------------------------------------------------------------------------------------------
+template <class Tab>
+__device__ __forceinline__ void showdown_body(const Tab& tab, const uint64_t* __restrict__ boards, const uint64_t* __restrict__ holes,
+                                              const uint32_t* __restrict__ live, int64_t n_games, int P,
+                                              uint32_t* __restrict__ winners, uint16_t* __restrict__ ranks)
+{
+    const HashParams hp = c_hp;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_games; g += nthr) {
+        const uint32_t lv = live ? live[g] : ((1u << P) - 1u);
+        const bool solo = __popc(lv) == 1;   // env/game.py:664-665: a lone player wins unevaluated
+        const uint64_t board = boards[g];
+        uint32_t best = 0xFFFFu, win = 0;
+        for (int p = 0; p < P; p++) {
+            uint32_t r = 0;
+            if ((lv >> p & 1) && !solo) {
+                r = eval7(board | holes[g * P + p], tab, hp);
+                if (r <= best) {
+                    if (r < best) { best = r; win = 0; }
+                    win |= 1u << p;
+                }
+            }
+            if (ranks) ranks[g * P + p] = (uint16_t)r;
+        }
+        winners[g] = solo ? lv : win;
+    }
+}
+
+__global__ void __launch_bounds__(kCtaThreads, 1)
+k_showdown_smem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict__ boards, const uint64_t* __restrict__ holes,
+                const uint32_t* __restrict__ live, int64_t n_games, int P, uint32_t* __restrict__ winners, uint16_t* __restrict__ ranks)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    stage_tables(smem, g_tab, reinterpret_cast<uint64_t*>(smem + kSmemTab));
+    const SharedTab tab{(uint32_t)__cvta_generic_to_shared(smem)};
+    showdown_body(tab, boards, holes, live, n_games, P, winners, ranks);
+}
+
+__global__ void __launch_bounds__(256)
+k_showdown_gmem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict__ boards, const uint64_t* __restrict__ holes,
+                const uint32_t* __restrict__ live, int64_t n_games, int P, uint32_t* __restrict__ winners, uint16_t* __restrict__ ranks)
+{
+    const GlobalTab tab{g_tab};
+    showdown_body(tab, boards, holes, live, n_games, P, winners, ranks);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: determinisation deals (GameEnv.new_random, env/game.py:119-163)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_deal(const uint64_t* __restrict__ known, int64_t n, int need, uint64_t seed, uint64_t sample, uint32_t stream_base,
+       uint8_t* __restrict__ cards_out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Dealt d = deal_cards(known[i] & CARD_BITS, seed, sample, stream_base + (uint32_t)i, need);
+    for (int k = 0; k < need; k++) cards_out[i * need + k] = (uint8_t)pos_to_id(d.get(k, need));
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: per-device context, error plumbing, launches
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kMaxDevices = 64;
+
+struct DevCtx {
+    std::once_flag once;
+    int status = PHE_ENODEVICE;
+    uint16_t* d_image = nullptr;
+    int sm_count = 0;
+};
+
+DevCtx g_ctx[kMaxDevices];
+std::atomic<uint64_t> g_launches{0};
+thread_local char t_cuda_err[256] = "";
+
+std::once_flag g_image_once;
+std::vector<uint16_t> g_image;
+HashParams g_hp;
+uint32_t g_binom[53 * 8];
+bool g_image_ok = false;
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    snprintf(t_cuda_err, sizeof t_cuda_err, "%s: %s", what, cudaGetErrorString(e));
+    return PHE_ECUDA;
+}
+
+#define PHE_CUDA(call)                                      \
+    do {                                                    \
+        cudaError_t e__ = (call);                           \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+void init_device(int device)
+{
+    DevCtx& cx = g_ctx[device];
+    std::call_once(g_image_once, [] {
+        g_image.resize(TAB_U16);
+        g_image_ok = build_table_image(g_image.data(), &g_hp);
+        build_binom(g_binom);
+    });
+    if (!g_image_ok) { cx.status = PHE_EINVAL; return; }
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { cx.status = cuda_fail(e, "cudaGetDeviceProperties"); return; }
+    if (prop.major != 10) {
+        snprintf(t_cuda_err, sizeof t_cuda_err, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        cx.status = PHE_ENODEVICE;
+        return;
+    }
+    cx.sm_count = prop.multiProcessorCount;
+    auto chk = [&](cudaError_t err, const char* what) {
+        if (err != cudaSuccess && cx.status == PHE_OK) cx.status = cuda_fail(err, what);
+    };
+    cx.status = PHE_OK;
+    chk(cudaSetDevice(device), "cudaSetDevice");
+    chk(cudaMalloc(&cx.d_image, TAB_BYTES), "cudaMalloc(tables)");
+    chk(cudaMemcpy(cx.d_image, g_image.data(), TAB_BYTES, cudaMemcpyHostToDevice), "cudaMemcpy(tables)");
+    chk(cudaMemcpyToSymbol(c_hp, &g_hp, sizeof g_hp), "cudaMemcpyToSymbol(c_hp)");
+    chk(cudaMemcpyToSymbol(c_binom, g_binom, sizeof g_binom), "cudaMemcpyToSymbol(c_binom)");
+    chk(cudaFuncSetAttribute(k_eval7_smem<PHE_LAYOUT_IDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr eval7 ids");
+    chk(cudaFuncSetAttribute(k_eval7_smem<PHE_LAYOUT_MASKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr eval7 masks");
+    chk(cudaFuncSetAttribute(k_enum7, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEnum), "attr enum7");
+    chk(cudaFuncSetAttribute(k_equity_mc_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr equity_mc");
+    chk(cudaFuncSetAttribute(k_equity_plan_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr equity_plan");
+    chk(cudaFuncSetAttribute(k_showdown_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr showdown");
+}
+
+// context of the current device, initialising it on first use
+int current_ctx(DevCtx** out)
+{
+    int dev = 0;
+    PHE_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return PHE_ENODEVICE;
+    DevCtx& cx = g_ctx[dev];
+    std::call_once(cx.once, init_device, dev);
+    if (cx.status != PHE_OK) return cx.status;
+    *out = &cx;
+    return PHE_OK;
+}
+
+int after_launch(const char* what)
+{
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    return PHE_OK;
+}
+
+// growable device scratch for the *_host entry points (one per host thread)
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+    int dev = -1;
+    int ensure(size_t bytes)
+    {
+        int d = 0;
+        PHE_CUDA(cudaGetDevice(&d));
+        if (p && d == dev && cap >= bytes) return PHE_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes < 4096 ? 4096 : bytes;
+        PHE_CUDA(cudaMalloc(&p, want));
+        cap = want; dev = d;
+        return PHE_OK;
+    }
+};
+thread_local Scratch t_in, t_out, t_aux;
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" {
+
+const char* phe_strerror(int status)
+{
+    switch (status) {
+        case PHE_OK: return "ok";
+        case PHE_EINVAL: return "invalid argument";
+        case PHE_ECUDA: return "CUDA error";
+        case PHE_ENODEVICE: return "no usable sm_100 device";
+        case PHE_EPLAN: return "equity plan not expressible";
+        case PHE_ENOMEM: return "out of memory";
+        default: return "unknown status";
+    }
+}
+
+const char* phe_last_cuda_error(void) { return t_cuda_err; }
+int phe_version(void) { return 100; }
+uint64_t phe_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int phe_init(int device)
+{
+    if (device < 0 || device >= kMaxDevices) return PHE_EINVAL;
+    int n = 0;
+    PHE_CUDA(cudaGetDeviceCount(&n));
+    if (device >= n) return PHE_ENODEVICE;
+    PHE_CUDA(cudaSetDevice(device));
+    DevCtx* cx = nullptr;
+    return current_ctx(&cx);
+}
+
+// ---- eval7 -------------------------------------------------------------------------------------
+static constexpr int64_t kSmallBatch = 1 << 16;   // below this the table image is read through L1/L2
+
+int phe_eval7(const void* hands, int layout, int64_t n, uint16_t* out, void* stream)
+{
+    if (n < 0 || (layout != PHE_LAYOUT_IDS && layout != PHE_LAYOUT_MASKS)) return PHE_EINVAL;
+    if (n == 0) return PHE_OK;
+    if (!hands || !out) return PHE_EINVAL;
+    DevCtx* cx = nullptr;
+    int rc = current_ctx(&cx);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n < kSmallBatch) {
+        const unsigned blocks = (unsigned)((n + 255) / 256);
+        if (layout == PHE_LAYOUT_IDS) k_eval7_gmem<PHE_LAYOUT_IDS><<<blocks, 256, 0, st>>>(cx->d_image, hands, n, out);
+        else k_eval7_gmem<PHE_LAYOUT_MASKS><<<blocks, 256, 0, st>>>(cx->d_image, hands, n, out);
+    } else {
+        if (layout == PHE_LAYOUT_IDS) k_eval7_smem<PHE_LAYOUT_IDS><<<cx->sm_count, kCtaThreads, kSmemTabOnly, st>>>(cx->d_image, hands, n, out);
+        else k_eval7_smem<PHE_LAYOUT_MASKS><<<cx->sm_count, kCtaThreads, kSmemTabOnly, st>>>(cx->d_image, hands, n, out);
+    }
+    return after_launch("eval7 launch");
+}
+
+int phe_eval7_host(const void* hands, int layout, int64_t n, uint16_t* out)
+{
+    if (n < 0 || (layout != PHE_LAYOUT_IDS && layout != PHE_LAYOUT_MASKS)) return PHE_EINVAL;
+    if (n == 0) return PHE_OK;
+    if (!hands || !out) return PHE_EINVAL;
+    const size_t in_bytes = (size_t)n * (layout == PHE_LAYOUT_IDS ? 7 : 8);
+    int rc;
+    if ((rc = t_in.ensure(in_bytes)) || (rc = t_out.ensure((size_t)n * 2))) return rc;
+    PHE_CUDA(cudaMemcpyAsync(t_in.p, hands, in_bytes, cudaMemcpyHostToDevice, 0));
+    if ((rc = phe_eval7(t_in.p, layout, n, static_cast<uint16_t*>(t_out.p), nullptr))) return rc;
+    PHE_CUDA(cudaMemcpyAsync(out, t_out.p, (size_t)n * 2, cudaMemcpyDeviceToHost, 0));
+    PHE_CUDA(cudaStreamSynchronize(0));
+    return PHE_OK;
+}
+
+// ---- enum7 -------------------------------------------------------------------------------------
+int phe_enum7(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin, uint64_t comb_end, void* stream)
+{
+    if (comb_begin > comb_end || comb_end > PHE_NUM_HANDS_7) return PHE_EINVAL;
+    if (comb_begin == comb_end || (!hist9 && !hist7463)) return PHE_OK;
+    DevCtx* cx = nullptr;
+    int rc = current_ctx(&cx);
+    if (rc) return rc;
+    const uint64_t total = comb_end - comb_begin;
+    uint64_t ctas = (total + kCtaThreads * 64 - 1) / (kCtaThreads * 64);
+    if (ctas > (uint64_t)cx->sm_count) ctas = cx->sm_count;
+    k_enum7<<<(unsigned)ctas, kCtaThreads, kSmemEnum, static_cast<cudaStream_t>(stream)>>>(
+        cx->d_image, reinterpret_cast<unsigned long long*>(hist9), reinterpret_cast<unsigned long long*>(hist7463), comb_begin, comb_end);
+    return after_launch("enum7 launch");
+}
+
+int phe_enum7_host(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin, uint64_t comb_end)
+{
+    if (comb_begin > comb_end || comb_end > PHE_NUM_HANDS_7) return PHE_EINVAL;
+    int rc;
+    const size_t bytes = (size_t)(9 + kHistBins) * 8;
+    if ((rc = t_out.ensure(bytes))) return rc;
+    uint64_t* d9 = static_cast<uint64_t*>(t_out.p);
+    uint64_t* d7 = d9 + 9;
+    PHE_CUDA(cudaMemsetAsync(t_out.p, 0, bytes, 0));
+    if ((rc = phe_enum7(d9, d7, comb_begin, comb_end, nullptr))) return rc;
+    std::vector<uint64_t> tmp(9 + kHistBins);
+    PHE_CUDA(cudaMemcpyAsync(tmp.data(), t_out.p, bytes, cudaMemcpyDeviceToHost, 0));
+    PHE_CUDA(cudaStreamSynchronize(0));
+    if (hist9) for (int i = 0; i < 9; i++) hist9[i] += tmp[i];
+    if (hist7463) for (int i = 0; i < kHistBins; i++) hist7463[i] += tmp[9 + i];
+    return PHE_OK;
+}
+
+// ---- equity_mc ---------------------------------------------------------------------------------
+int phe_equity_mc(const uint64_t* states, int64_t n_states, int n_opp, uint64_t rollouts, uint64_t sample_offset, uint64_t seed,
+                  uint32_t state_index_base, uint64_t* wtl, void* stream)
+{
+    if (n_states < 0 || n_opp < 1 || n_opp > PHE_MAX_PLAYERS - 1) return PHE_EINVAL;
+    if (n_states == 0 || rollouts == 0) return PHE_OK;
+    if (!states || !wtl) return PHE_EINVAL;
+    DevCtx* cx = nullptr;
+    int rc = current_ctx(&cx);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // samples per warp item: aim at >= 4 items per resident warp, 32..8192, multiple of 32
+    const double total = (double)n_states * (double)rollouts;
+    const uint64_t warps = (uint64_t)cx->sm_count * (kCtaThreads / 32);
+    uint64_t chunk = (uint64_t)(total / (double)(warps * 4));
+    chunk = (chunk + 31) & ~(uint64_t)31;
+    if (chunk < 32) chunk = 32;
+    if (chunk > 8192) chunk = 8192;
+    if (chunk > ((rollouts + 31) & ~(uint64_t)31)) chunk = (rollouts + 31) & ~(uint64_t)31;
+    const uint64_t items = (uint64_t)n_states * ((rollouts + chunk - 1) / chunk);
+    const auto* sp = reinterpret_cast<const ulonglong2*>(states);
+    auto* wp = reinterpret_cast<unsigned long long*>(wtl);
+    if (total < 1.0e6) {
+        uint64_t blocks = (items + 7) / 8;   // 8 warps per 256-thread block
+        if (blocks > (uint64_t)cx->sm_count * 8) blocks = (uint64_t)cx->sm_count * 8;
+        k_equity_mc_gmem<<<(unsigned)blocks, 256, 0, st>>>(cx->d_image, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk);
+    } else {
+        uint64_t ctas = (items + 31) / 32;
+        if (ctas > (uint64_t)cx->sm_count) ctas = cx->sm_count;
+        k_equity_mc_smem<<<(unsigned)ctas, kCtaThreads, kSmemTabOnly, st>>>(cx->d_image, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk);
+    }
+    return after_launch("equity_mc launch");
+}
+
+int phe_equity_mc_host(const uint64_t* states, int64_t n_states, int n_opp, uint64_t rollouts, uint64_t sample_offset, uint64_t seed,
+                       uint32_t state_index_base, uint64_t* wtl)
+{
+    if (n_states < 0) return PHE_EINVAL;
+    if (n_states == 0) return PHE_OK;
+    if (!states || !wtl) return PHE_EINVAL;
+    int rc;
+    const size_t in_bytes = (size_t)n_states * 16, out_bytes = (size_t)n_states * 24;
+    if ((rc = t_in.ensure(in_bytes)) || (rc = t_out.ensure(out_bytes))) return rc;
+    PHE_CUDA(cudaMemcpyAsync(t_in.p, states, in_bytes, cudaMemcpyHostToDevice, 0));
+    PHE_CUDA(cudaMemsetAsync(t_out.p, 0, out_bytes, 0));
+    if ((rc = phe_equity_mc(static_cast<const uint64_t*>(t_in.p), n_states, n_opp, rollouts, sample_offset, seed, state_index_base,
+                            static_cast<uint64_t*>(t_out.p), nullptr)))
+        return rc;
+    std::vector<uint64_t> tmp((size_t)n_states * 3);
+    PHE_CUDA(cudaMemcpyAsync(tmp.data(), t_out.p, out_bytes, cudaMemcpyDeviceToHost, 0));
+    PHE_CUDA(cudaStreamSynchronize(0));
+    for (size_t i = 0; i < tmp.size(); i++) wtl[i] += tmp[i];
+    return PHE_OK;
+}
+
+// ---- equity_plan -------------------------------------------------------------------------------
+uint64_t phe_plan_num_deals(int n_exist, const int32_t* plan, int n_steps)
+{
+    PlanDesc pd;
+    return parse_plan(n_exist, plan, n_steps, &pd) ? plan_num_deals(pd) : 0;
+}
+
+int phe_equity_plan(const uint8_t* exist, int n_exist, int64_t n_tasks, const int32_t* plan, int n_steps, uint64_t seed,
+                    uint32_t stream_base, uint64_t* wtl, void* stream)
+{
+    if (n_tasks < 0) return PHE_EINVAL;
+    PlanDesc pd;
+    if (!parse_plan(n_exist, plan, n_steps, &pd)) return PHE_EPLAN;
+    if (n_tasks == 0) return PHE_OK;
+    if (!exist || !wtl) return PHE_EINVAL;
+    DevCtx* cx = nullptr;
+    int rc = current_ctx(&cx);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const double deals = (double)n_tasks * (double)plan_num_deals(pd);
+    const uint64_t threads = (uint64_t)n_tasks * pd.n_leaves;
+    auto* wp = reinterpret_cast<unsigned long long*>(wtl);
+    if (deals < 2.0e6) {
+        uint64_t blocks = (threads + 255) / 256;
+        if (blocks > (uint64_t)cx->sm_count * 8) blocks = (uint64_t)cx->sm_count * 8;
+        k_equity_plan_gmem<<<(unsigned)blocks, 256, 0, st>>>(cx->d_image, exist, n_tasks, pd, seed, stream_base, wp);
+    } else {
+        uint64_t ctas = (threads + kCtaThreads - 1) / kCtaThreads;
+        if (ctas > (uint64_t)cx->sm_count) ctas = cx->sm_count;
+        k_equity_plan_smem<<<(unsigned)ctas, kCtaThreads, kSmemTabOnly, st>>>(cx->d_image, exist, n_tasks, pd, seed, stream_base, wp);
+    }
+    return after_launch("equity_plan launch");
+}
+
+int phe_equity_plan_host(const uint8_t* exist, int n_exist, int64_t n_tasks, const int32_t* plan, int n_steps, uint64_t seed,
+                         uint32_t stream_base, uint64_t* wtl)
+{
+    if (n_tasks < 0) return PHE_EINVAL;
+    PlanDesc pd;
+    if (!parse_plan(n_exist, plan, n_steps, &pd)) return PHE_EPLAN;
+    if (n_tasks == 0) return PHE_OK;
+    if (!exist || !wtl) return PHE_EINVAL;
+    int rc;
+    const size_t in_bytes = (size_t)n_tasks * 8, out_bytes = (size_t)n_tasks * 24;
+    if ((rc = t_in.ensure(in_bytes)) || (rc = t_out.ensure(out_bytes))) return rc;
+    PHE_CUDA(cudaMemcpyAsync(t_in.p, exist, in_bytes, cudaMemcpyHostToDevice, 0));
+    PHE_CUDA(cudaMemsetAsync(t_out.p, 0, out_bytes, 0));
+    if ((rc = phe_equity_plan(static_cast<const uint8_t*>(t_in.p), n_exist, n_tasks, plan, n_steps, seed, stream_base,
+                              static_cast<uint64_t*>(t_out.p), nullptr)))
+        return rc;
+    std::vector<uint64_t> tmp((size_t)n_tasks * 3);
+    PHE_CUDA(cudaMemcpyAsync(tmp.data(), t_out.p, out_bytes, cudaMemcpyDeviceToHost, 0));
+    PHE_CUDA(cudaStreamSynchronize(0));
+    for (size_t i = 0; i < tmp.size(); i++) wtl[i] += tmp[i];
+    return PHE_OK;
+}
+
+// ---- showdown ----------------------------------------------------------------------------------
+int phe_showdown(const uint64_t* boards, const uint64_t* holes, const uint32_t* live, int64_t n_games, int n_players,
+                 uint32_t* winners_out, uint16_t* ranks_out, void* stream)
+{
+    if (n_games < 0 || n_players < 1 || n_players > PHE_MAX_PLAYERS) return PHE_EINVAL;
+    if (n_games == 0) return PHE_OK;
+    if (!boards || !holes || !winners_out) return PHE_EINVAL;
+    DevCtx* cx = nullptr;
+    int rc = current_ctx(&cx);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_games * n_players < kSmallBatch) {
+        const unsigned blocks = (unsigned)((n_games + 255) / 256);
+        k_showdown_gmem<<<blocks, 256, 0, st>>>(cx->d_image, boards, holes, live, n_games, n_players, winners_out, ranks_out);
+    } else {
+        uint64_t ctas = ((uint64_t)n_games + kCtaThreads - 1) / kCtaThreads;
+        if (ctas > (uint64_t)cx->sm_count) ctas = cx->sm_count;
+        k_showdown_smem<<<(unsigned)ctas, kCtaThreads, kSmemTabOnly, st>>>(cx->d_image, boards, holes, live, n_games, n_players, winners_out, ranks_out);
+    }
+    return after_launch("showdown launch");
+}
+
+int phe_showdown_host(const uint64_t* boards, const uint64_t* holes, const uint32_t* live, int64_t n_games, int n_players,
+                      uint32_t* winners_out, uint16_t* ranks_out)
+{
+    if (n_games < 0 || n_players < 1 || n_players > PHE_MAX_PLAYERS) return PHE_EINVAL;
+    if (n_games == 0) return PHE_OK;
+    if (!boards || !holes || !winners_out) return PHE_EINVAL;
+    const size_t G = (size_t)n_games, P = (size_t)n_players;
+    const size_t o_boards = 0, o_holes = align256(G * 8), o_live = o_holes + align256(G * P * 8);
+    const size_t in_bytes = o_live + align256(G * 4);
+    const size_t o_win = 0, o_ranks = align256(G * 4), out_bytes = o_ranks + align256(G * P * 2);
+    int rc;
+    if ((rc = t_in.ensure(in_bytes)) || (rc = t_out.ensure(out_bytes))) return rc;
+    char* di = static_cast<char*>(t_in.p);
+    char* dout = static_cast<char*>(t_out.p);
+    PHE_CUDA(cudaMemcpyAsync(di + o_boards, boards, G * 8, cudaMemcpyHostToDevice, 0));
+    PHE_CUDA(cudaMemcpyAsync(di + o_holes, holes, G * P * 8, cudaMemcpyHostToDevice, 0));
+    if (live) PHE_CUDA(cudaMemcpyAsync(di + o_live, live, G * 4, cudaMemcpyHostToDevice, 0));
+    if ((rc = phe_showdown(reinterpret_cast<uint64_t*>(di + o_boards), reinterpret_cast<uint64_t*>(di + o_holes),
+                           live ? reinterpret_cast<uint32_t*>(di + o_live) : nullptr, n_games, n_players,
+                           reinterpret_cast<uint32_t*>(dout + o_win), ranks_out ? reinterpret_cast<uint16_t*>(dout + o_ranks) : nullptr, nullptr)))
+        return rc;
+    PHE_CUDA(cudaMemcpyAsync(winners_out, dout + o_win, G * 4, cudaMemcpyDeviceToHost, 0));
+    if (ranks_out) PHE_CUDA(cudaMemcpyAsync(ranks_out, dout + o_ranks, G * P * 2, cudaMemcpyDeviceToHost, 0));
+    PHE_CUDA(cudaStreamSynchronize(0));
+    return PHE_OK;
+}
+
+// ---- deal --------------------------------------------------------------------------------------
+int phe_deal(const uint64_t* known, int64_t n, int need, uint64_t seed, uint64_t sample_offset, uint32_t stream_base,
+             uint8_t* cards_out, void* stream)
+{
+    if (n < 0 || need < 1 || need > MAX_DEAL) return PHE_EINVAL;
+    if (n == 0) return PHE_OK;
+    if (!known || !cards_out) return PHE_EINVAL;
+    DevCtx* cx = nullptr;
+    int rc = current_ctx(&cx);
+    if (rc) return rc;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    k_deal<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(known, n, need, seed, sample_offset, stream_base, cards_out);
+    return after_launch("deal launch");
+}
+
+int phe_deal_host(const uint64_t* known, int64_t n, int need, uint64_t seed, uint64_t sample_offset, uint32_t stream_base,
+                  uint8_t* cards_out)
+{
+    if (n < 0 || need < 1 || need > MAX_DEAL) return PHE_EINVAL;
+    if (n == 0) return PHE_OK;
+    if (!known || !cards_out) return PHE_EINVAL;
+    int rc;
+    if ((rc = t_in.ensure((size_t)n * 8)) || (rc = t_out.ensure((size_t)n * need))) return rc;
+    PHE_CUDA(cudaMemcpyAsync(t_in.p, known, (size_t)n * 8, cudaMemcpyHostToDevice, 0));
+    if ((rc = phe_deal(static_cast<const uint64_t*>(t_in.p), n, need, seed, sample_offset, stream_base, static_cast<uint8_t*>(t_out.p), nullptr)))
+        return rc;
+    PHE_CUDA(cudaMemcpyAsync(cards_out, t_out.p, (size_t)n * need, cudaMemcpyDeviceToHost, 0));
+    PHE_CUDA(cudaStreamSynchronize(0));
+    return PHE_OK;
+}
+
+}  // extern "C"

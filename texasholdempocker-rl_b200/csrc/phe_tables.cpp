@@ -1,0 +1,250 @@
+// phe_tables.cpp -- builds the lookup-table image the kernels stage into shared memory.
+//
+// Product code (not the oracle): ranks are computed analytically from the canonical
+// 7462-class numbering that phevaluator.evaluate_cards returns (reference call site
+// env/game.py:675; category blocks SF 1-10, quads 11-166, full house 167-322, flush 323-1599,
+// straight 1600-1609, trips 1610-2467, two pair 2468-3325, pair 3326-6185, high card 6186-7462).
+// tests/ compare the result with the independent sort-based oracle on every table entry.
+//
+// Image layout (uint16): NOFLUSH[65536] | DISP[8192] | FLUSH[8192]  (see phe_core.cuh).
+//   NOFLUSH is addressed by a two-level perfect hash (hash-and-displace) of the bit-sliced rank
+//   multiplicities (b0, b1, b2) the evaluator derives from a card-set word.
+#include "phe_tables.h"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace phe {
+
+static uint32_t binom_u32(int n, int k)
+{
+    if (k < 0 || n < k) return 0;
+    uint64_t r = 1;
+    for (int i = 1; i <= k; i++) r = r * (uint64_t)(n - k + i) / (uint64_t)i;
+    return (uint32_t)r;
+}
+
+void build_binom(uint32_t out[53 * 8])
+{
+    for (int n = 0; n <= 52; n++)
+        for (int k = 0; k < 8; k++) out[n * 8 + k] = binom_u32(n, k);
+}
+
+// highest card of a straight contained in rank set m (wheel = 3), or -1
+static int straight_high(uint32_t m)
+{
+    for (int h = 12; h >= 4; h--)
+        if (((m >> (h - 4)) & 0x1F) == 0x1F) return h;
+    if ((m & 0x100F) == 0x100F) return 3;
+    return -1;
+}
+
+// keep the `k` highest set bits of m
+static uint32_t top_bits(uint32_t m, int k)
+{
+    uint32_t out = 0;
+    for (int r = 12; r >= 0 && k > 0; r--)
+        if (m >> r & 1) { out |= 1u << r; k--; }
+    return out;
+}
+
+// strongest-first index of a k-subset (as a bit set over n ranks) among all C(n,k) subsets,
+// ordered by comparing the highest element first
+static uint32_t subset_index_desc(uint32_t m, int n, int k)
+{
+    uint32_t colex = 0;
+    int i = 0;
+    for (int r = 0; r < n; r++)
+        if (m >> r & 1) { i++; colex += binom_u32(r, i); }
+    return binom_u32(n, k) - 1 - colex;
+}
+
+// remove bit positions listed in `drop` (a bit set) and close the gaps
+static uint32_t squeeze(uint32_t m, uint32_t drop)
+{
+    uint32_t out = 0; int o = 0;
+    for (int r = 0; r < 13; r++) {
+        if (drop >> r & 1) continue;
+        if (m >> r & 1) out |= 1u << o;
+        o++;
+    }
+    return out;
+}
+
+static int highest_bit(uint32_t m) { return m ? 31 - __builtin_clz(m) : -1; }
+
+struct FiveIndex {
+    // for 5-bit rank sets: index among the 1277 non-straight sets, strongest first
+    uint16_t idx[8192];
+    FiveIndex()
+    {
+        std::memset(idx, 0xFF, sizeof idx);
+        std::vector<uint32_t> sets;
+        for (uint32_t m = 0; m < 8192; m++)
+            if (__builtin_popcount(m) == 5) sets.push_back(m);
+        std::sort(sets.begin(), sets.end(), [](uint32_t a, uint32_t b) { return a > b; });   // numeric desc == highest card first
+        uint16_t run = 0;
+        for (uint32_t m : sets)
+            if (straight_high(m) < 0) idx[m] = run++;
+    }
+};
+
+static const FiveIndex& five_index()
+{
+    static const FiveIndex f;
+    return f;
+}
+
+uint16_t flush_rank(uint32_t lane)
+{
+    const int h = straight_high(lane);
+    if (h >= 0) return (uint16_t)(1 + (12 - h));                       // straight flush
+    return (uint16_t)(323 + five_index().idx[top_bits(lane, 5)]);      // plain flush
+}
+
+// rank of a non-flush 7-card hand from its rank multiplicities
+uint16_t noflush_rank(const uint8_t cnt[13])
+{
+    uint32_t any = 0, ge2 = 0, ge3 = 0, eq4 = 0;
+    for (int r = 0; r < 13; r++) {
+        if (cnt[r] >= 1) any |= 1u << r;
+        if (cnt[r] >= 2) ge2 |= 1u << r;
+        if (cnt[r] >= 3) ge3 |= 1u << r;
+        if (cnt[r] == 4) eq4 |= 1u << r;
+    }
+    if (eq4) {
+        const int q = highest_bit(eq4);
+        const uint32_t rest = any & ~(1u << q);
+        const uint32_t kick = squeeze(1u << highest_bit(rest), 1u << q);
+        return (uint16_t)(11 + (12 - q) * 12 + (11 - highest_bit(kick)));
+    }
+    if (ge3) {
+        const int t = highest_bit(ge3);
+        const uint32_t pairs = ge2 & ~(1u << t);
+        if (pairs) {
+            const uint32_t p = squeeze(1u << highest_bit(pairs), 1u << t);
+            return (uint16_t)(167 + (12 - t) * 12 + (11 - highest_bit(p)));
+        }
+    }
+    const int sh = straight_high(any);
+    if (sh >= 0) return (uint16_t)(1600 + (12 - sh));
+    if (ge3) {
+        const int t = highest_bit(ge3);
+        const uint32_t kick = squeeze(top_bits(any & ~(1u << t), 2), 1u << t);
+        return (uint16_t)(1610 + (12 - t) * 66 + subset_index_desc(kick, 12, 2));
+    }
+    if (__builtin_popcount(ge2) >= 2) {
+        const uint32_t two = top_bits(ge2, 2);
+        const uint32_t kick = squeeze(1u << highest_bit(any & ~two), two);
+        return (uint16_t)(2468 + subset_index_desc(two, 13, 2) * 11 + (10 - highest_bit(kick)));
+    }
+    if (ge2) {
+        const int p = highest_bit(ge2);
+        const uint32_t kick = squeeze(top_bits(any & ~(1u << p), 3), 1u << p);
+        return (uint16_t)(3326 + (12 - p) * 220 + subset_index_desc(kick, 12, 3));
+    }
+    return (uint16_t)(6186 + five_index().idx[top_bits(any, 5)]);
+}
+
+static void enum_counts(uint8_t cnt[13], int pos, int left, std::vector<NoflushKey>& out)
+{
+    if (pos == 13) {
+        if (left) return;
+        NoflushKey k; k.b0 = k.b1 = k.b2 = 0;
+        for (int r = 0; r < 13; r++) {
+            if (cnt[r] & 1) k.b0 |= 1u << r;
+            if (cnt[r] & 2) k.b1 |= 1u << r;
+            if (cnt[r] & 4) k.b2 |= 1u << r;
+        }
+        k.rank = noflush_rank(cnt);
+        out.push_back(k);
+        return;
+    }
+    for (int d = 0; d <= 4 && d <= left; d++) { cnt[pos] = (uint8_t)d; enum_counts(cnt, pos + 1, left - d, out); }
+    cnt[pos] = 0;
+}
+
+std::vector<NoflushKey> all_noflush_keys()
+{
+    std::vector<NoflushKey> v;
+    uint8_t cnt[13] = {0};
+    enum_counts(cnt, 0, 7, v);
+    return v;
+}
+
+static inline uint32_t key_of(const NoflushKey& k) { return (k.b0 & 0xFFFFu) | (k.b1 << 16); }
+
+// hash-and-displace: bucket = h1 >> 19, slot = ((h2 >> 16) + DISP[bucket]) & 0xFFFF
+static bool try_build(const std::vector<NoflushKey>& keys, const HashParams& hp, uint16_t* image)
+{
+    const size_t n = keys.size();
+    std::vector<uint32_t> bucket(n), pos(n);
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t key = key_of(keys[i]);
+        bucket[i] = (key * hp.a1 + keys[i].b2 * hp.b1) >> 19;
+        pos[i] = (key * hp.a2 + keys[i].b2 * hp.b2) >> 16;
+    }
+    std::vector<std::vector<uint32_t>> members(DISP_SIZE);
+    for (size_t i = 0; i < n; i++) members[bucket[i]].push_back((uint32_t)i);
+    // two keys of one bucket must not share a slot offset
+    for (auto& mb : members) {
+        std::vector<uint32_t> p;
+        for (uint32_t i : mb) p.push_back(pos[i]);
+        std::sort(p.begin(), p.end());
+        if (std::adjacent_find(p.begin(), p.end()) != p.end()) return false;
+    }
+    std::vector<uint32_t> order(DISP_SIZE);
+    for (uint32_t b = 0; b < DISP_SIZE; b++) order[b] = b;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return members[x].size() > members[y].size(); });
+    std::vector<uint8_t> taken(NOFLUSH_SIZE, 0);
+    uint16_t* noflush = image;
+    uint16_t* disp = image + OFF_DISP;
+    std::memset(noflush, 0, NOFLUSH_SIZE * sizeof(uint16_t));
+    std::memset(disp, 0, DISP_SIZE * sizeof(uint16_t));
+    for (uint32_t b : order) {
+        const auto& mb = members[b];
+        if (mb.empty()) break;
+        bool placed = false;
+        for (uint32_t d = 0; d < NOFLUSH_SIZE && !placed; d++) {
+            bool ok = true;
+            for (uint32_t i : mb)
+                if (taken[(pos[i] + d) & 0xFFFFu]) { ok = false; break; }
+            if (!ok) continue;
+            for (uint32_t i : mb) {
+                const uint32_t s = (pos[i] + d) & 0xFFFFu;
+                taken[s] = 1;
+                noflush[s] = keys[i].rank;
+            }
+            disp[b] = (uint16_t)d;
+            placed = true;
+        }
+        if (!placed) return false;
+    }
+    return true;
+}
+
+bool build_table_image(uint16_t* image, HashParams* hp_out)
+{
+    const std::vector<NoflushKey> keys = all_noflush_keys();
+    if (keys.size() != 49205) return false;
+    uint16_t* flush = image + OFF_FLUSH;
+    for (uint32_t m = 0; m < FLUSH_SIZE; m++) {
+        const int pc = __builtin_popcount(m);
+        flush[m] = (pc >= 5 && pc <= 7) ? flush_rank(m) : (uint16_t)0;
+    }
+    // deterministic multiplier search (first candidate normally succeeds)
+    uint64_t s = 0x9E3779B97F4A7C15ull;
+    for (int attempt = 0; attempt < 64; attempt++) {
+        uint32_t v[4];
+        for (int i = 0; i < 4; i++) {
+            s = s * 6364136223846793005ull + 1442695040888963407ull;
+            v[i] = (uint32_t)(s >> 32) | 1u;
+        }
+        HashParams hp{v[0], v[1], v[2], v[3]};
+        if (try_build(keys, hp, image)) { *hp_out = hp; return true; }
+    }
+    return false;
+}
+
+}  // namespace phe

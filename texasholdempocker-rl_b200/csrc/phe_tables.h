@@ -1,0 +1,25 @@
+// phe_tables.h -- host-side construction of the evaluator's lookup-table image.
+#pragma once
+#include <stdint.h>
+
+#include <vector>
+
+#include "phe_core.cuh"
+
+namespace phe {
+
+struct NoflushKey { uint32_t b0, b1, b2; uint16_t rank; };
+
+// C(n,k) for n <= 52, k <= 7, row-major [53][8]
+void build_binom(uint32_t out[53 * 8]);
+
+// rank of the best flush / straight flush inside one 13-bit suit lane with 5..7 bits set
+uint16_t flush_rank(uint32_t lane);
+// rank of a 7-card hand without a flush, from its 13 rank multiplicities (sum 7, each <= 4)
+uint16_t noflush_rank(const uint8_t cnt[13]);
+// all 49205 rank multisets with their bit-sliced keys and ranks
+std::vector<NoflushKey> all_noflush_keys();
+// fills image[TAB_U16] and the hash multipliers; false if no perfect hash was found
+bool build_table_image(uint16_t* image, HashParams* hp_out);
+
+}  // namespace phe

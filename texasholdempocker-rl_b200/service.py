@@ -1,0 +1,104 @@
+"""GPU equity service speaking the reference's task / result tuples.
+
+Replaces the pool of ``simulate_processes`` workers (env/workflow.py:102-227): same queue protocol, same
+``simulation_recurrent_param_dict`` plans, but tasks are drained in batches and each (round, batch) is one
+``phe_equity_plan`` launch.
+
+  task   (game_id, player_name, current_round, flop_cards, turn_cards, river_cards, player_hand_card)
+         (env/env.py:240; board entries are None for streets not reached)
+  result (game_id, player_name, current_round, num_estimation, game_result_sum)   (env/workflow.py:225)
+"""
+import logging
+import queue as _queue
+
+import numpy as np
+
+from .cardset import card_id
+from .equity import equity_plan, plan_num_deals
+
+_N_EXIST = {0: 2, 1: 5, 2: 6, 3: 7}
+
+
+def task_exist_ids(task):
+    """Known cards of a task in the reference's order (env/workflow.py:212-221)."""
+    _, _, rnd, flop, turn, river, hand = task
+    ids = [card_id(c) for c in hand]
+    if rnd > 0:
+        ids += [card_id(c) for c in flop]
+    if rnd > 1:
+        ids += [card_id(c) for c in turn]
+    if rnd > 2:
+        ids += [card_id(c) for c in river]
+    if len(ids) != _N_EXIST[rnd] or len(set(ids)) != len(ids):
+        raise ValueError(f"task for round {rnd} has {len(ids)} known cards / duplicates")
+    return ids
+
+
+def solve_tasks(tasks, simulation_recurrent_param_dict, seed=0, stream_base=0):
+    """Evaluate a list of task tuples; returns result tuples in task order."""
+    results = [None] * len(tasks)
+    by_round = {}
+    for i, t in enumerate(tasks):
+        by_round.setdefault(t[2], []).append(i)
+    for rnd, idxs in by_round.items():
+        plan, num_estimation = simulation_recurrent_param_dict[rnd]
+        exist = np.array([task_exist_ids(tasks[i]) for i in idxs], dtype=np.uint8)
+        wtl = equity_plan(exist, plan, seed=seed, stream_base=stream_base + idxs[0])
+        for row, i in enumerate(idxs):
+            n = int(wtl[row].sum())
+            # the reference asserts this too (env/workflow.py:223)
+            assert n == num_estimation, f"plan for round {rnd} generated {n} deals, config says {num_estimation}"
+            game_id, player_name = tasks[i][0], tasks[i][1]
+            results[i] = (game_id, player_name, rnd, num_estimation, float(int(wtl[row, 0]) - int(wtl[row, 2])))
+    return results
+
+
+def winning_probability(game_result_sum, num_estimation):
+    """env/workflow.py:247-251"""
+    return (game_result_sum / num_estimation) * 0.5 + 0.5
+
+
+def check_plans(simulation_recurrent_param_dict):
+    for rnd, (plan, num_estimation) in simulation_recurrent_param_dict.items():
+        n = plan_num_deals(_N_EXIST[rnd], plan)
+        if n != num_estimation:
+            raise ValueError(f"round {rnd}: plan yields {n} deals but num_estimation is {num_estimation}")
+
+
+def simulate_processes(in_queue, out_queue, simulation_recurrent_param_dict, pid, log_level,
+                       interrupt_callback=None, max_batch=4096, seed=0):
+    """Drop-in body for the reference's equity worker (same first five parameters, env/workflow.py:102).
+
+    Blocks on in_queue with a 0.1 s timeout like the reference, drains up to max_batch tasks, solves them on
+    the GPU and puts the result tuples on out_queue.  Returns when interrupt_callback() is true or a ``None``
+    task arrives.
+    """
+    logging.getLogger().setLevel(log_level)
+    logging.info(f"simulate_processes (B200) {pid} started")
+    check_plans(simulation_recurrent_param_dict)
+    served = 0
+    while True:
+        if interrupt_callback is not None and interrupt_callback():
+            return served
+        try:
+            first = in_queue.get(block=True, timeout=0.1)
+        except _queue.Empty:
+            continue
+        if first is None:
+            return served
+        batch = [first]
+        stop = False
+        while len(batch) < max_batch:
+            try:
+                t = in_queue.get(block=False)
+            except _queue.Empty:
+                break
+            if t is None:
+                stop = True
+                break
+            batch.append(t)
+        for r in solve_tasks(batch, simulation_recurrent_param_dict, seed=seed, stream_base=served):
+            out_queue.put(r)
+        served += len(batch)
+        if stop:
+            return served

@@ -1,0 +1,60 @@
+"""Multi-GPU sharding: one process per GPU, work split by sample index / combination index, one
+all-reduce(SUM) of the integer counts (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+
+Integer sums make the result bit-identical for any world size and any reduction order.
+"""
+import numpy as np
+
+from . import _native as N
+
+try:
+    import torch
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    torch = None
+    dist = None
+
+
+def shard_range(total, rank, world):
+    """Contiguous shard [begin, end) of range(total) for `rank` of `world`; shards tile the range exactly."""
+    total, rank, world = int(total), int(rank), int(world)
+    return total * rank // world, total * (rank + 1) // world
+
+
+def _world(group):
+    if dist is None or not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def sharded_equity_mc(states, n_opp, rollouts, seed, sample_offset=0, group=None, local_fn=None, reduce=True):
+    """Every rank holds the same `states`; rank r rolls samples shard_range(rollouts, r, world) and the
+    (win, tie, loss) counts are all-reduced.  local_fn(states, n_opp, rollouts, seed, sample_offset=...)
+    defaults to the CUDA path (tests inject the oracle there)."""
+    from .equity import equity_mc
+    fn = local_fn or equity_mc
+    rank, world = _world(group)
+    b, e = shard_range(rollouts, rank, world)
+    counts = fn(states, n_opp, e - b, seed, sample_offset=sample_offset + b)
+    if world > 1 and reduce:
+        t = counts if (torch is not None and isinstance(counts, torch.Tensor)) else torch.from_numpy(np.ascontiguousarray(counts))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        counts = t if isinstance(counts, torch.Tensor) else t.numpy()
+    return counts
+
+
+def sharded_enum7(group=None, local_fn=None, comb_begin=0, comb_end=N.NUM_HANDS_7, reduce=True):
+    """Rank r enumerates its contiguous slice of colex combination indices; histograms are all-reduced."""
+    from .evaluator import enumerate_c52_7
+    rank, world = _world(group)
+    b, e = shard_range(comb_end - comb_begin, rank, world)
+    if local_fn is None:
+        h9, h = enumerate_c52_7(comb_begin + b, comb_begin + e, device_out=True)
+    else:
+        h9, h = local_fn(comb_begin + b, comb_begin + e)
+    if world > 1 and reduce:
+        if not isinstance(h9, torch.Tensor):
+            h9, h = torch.from_numpy(np.ascontiguousarray(h9)), torch.from_numpy(np.ascontiguousarray(h))
+        dist.all_reduce(h9, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
+    return h9, h
