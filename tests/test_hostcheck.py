@@ -104,3 +104,22 @@ def test_plans(hostcheck, oracle, text, rnd):
         assert hostcheck.hc_equity_plan(vp(e), len(e), vp(p), len(p), 5, 2, vp(out)) == 0
         assert tuple(int(x) for x in out) == oracle.equity_plan(oracle.ids(text), plan, seed=5, stream=2)
         assert int(out[3]) == plans[rnd][1] == hostcheck.hc_plan_num_deals(len(e), vp(p), len(p))
+
+
+@pytest.mark.parametrize("b,e", [(0, 1), (0, 7), (5, 6), (133784559, 133784560), (12345, 1234567), (133000000, 133784560)])
+def test_enum_block_walk(hostcheck, oracle, b, e):
+    """phe_enum.cuh: block setup / successor / per-hand rank, walked serially the way one warp walks its slice."""
+    hostcheck.hc_enum7.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
+    h = np.zeros(7463, dtype=np.uint64)
+    hostcheck.hc_enum7(b, e, vp(h))
+    o9, oh = oracle.enum7(b, e, nthreads=2)
+    assert (h.astype(np.int64) == oh).all()
+
+
+def test_enum_block_walk_full(hostcheck):
+    import json, os
+    from conftest import GOLDEN
+    hostcheck.hc_enum7.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
+    h = np.zeros(7463, dtype=np.uint64)
+    hostcheck.hc_enum7(0, 133784560, vp(h))
+    assert h.tolist() == json.load(open(os.path.join(GOLDEN, "hist7463.json")))["hist7463"]

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "phe_core.cuh"
+#include "phe_enum.cuh"
 #include "phe_plan.h"
 #include "phe_tables.h"
 
@@ -16,6 +17,8 @@ using namespace phe;
 static std::vector<uint16_t> g_image;
 static HashParams g_hp;
 static uint32_t g_binom[53 * 8];
+static std::vector<unsigned char> g_enum_image;
+static std::vector<uint64_t> g_trimask;
 
 extern "C" {
 
@@ -25,6 +28,9 @@ int hc_init(void)
     g_image.resize(TAB_U16);
     if (!build_table_image(g_image.data(), &g_hp)) { g_image.clear(); return -1; }
     build_binom(g_binom);
+    g_enum_image.resize(ENUM_IMG_BYTES);
+    g_trimask.resize(N_TRIPLES);
+    build_enum_image(g_enum_image.data(), g_trimask.data());
     return 0;
 }
 
@@ -92,6 +98,30 @@ int hc_equity_plan(const uint8_t* exist, int n_exist, const int32_t* plan, int n
         }
     }
     return 0;
+}
+
+// serial emulation of the enumeration kernel's warp loop over the colex range [begin, end)
+void hc_enum7(uint64_t begin, uint64_t end, uint64_t* hist7463)
+{
+    if (begin >= end) return;
+    Binom C{g_binom};
+    EnumImage img{g_enum_image.data(), g_trimask.data()};
+    int c[7];
+    colex_unrank7(begin, C, c);
+    int c3 = c[3], c4 = c[4], c5 = c[5], c6 = c[6];
+    uint64_t remaining = end - begin;
+    uint32_t t_start = C(c[2], 3) + C(c[1], 2) + (uint32_t)c[0];
+    for (;;) {
+        EnumBlock b;
+        enum_block_setup(c3, c4, c5, c6, C, b);
+        uint64_t stop = b.ntriples;
+        if (stop > t_start + remaining) stop = t_start + remaining;
+        for (uint32_t t = t_start; t < stop; t++) hist7463[enum_hand_rank(img, b, t)]++;
+        remaining -= stop - t_start;
+        if (!remaining) break;
+        t_start = 0;
+        enum_block_next(c3, c4, c5, c6);
+    }
 }
 
 uint64_t hc_plan_num_deals(int n_exist, const int32_t* plan, int n_steps)

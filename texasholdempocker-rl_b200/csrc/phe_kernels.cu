@@ -15,6 +15,7 @@
 
 #include "../../include/phe_b200.h"
 #include "phe_core.cuh"
+#include "phe_enum.cuh"
 #include "phe_plan.h"
 #include "phe_tables.h"
 
@@ -30,16 +31,20 @@ static constexpr int kCtaThreads = 1024;
 static constexpr int kHistBins = PHE_NUM_RANKS + 1;                 // 7463, bin = rank
 static constexpr int kHistBinsPad = 7464;
 static constexpr uint32_t kSmemTab = TAB_BYTES;                       // 163,840
-static constexpr uint32_t kSmemEnum = kSmemTab + kHistBinsPad * 4 + 9 * 8 + 16;
+static constexpr uint32_t kEnumHistOff = ENUM_IMG_BYTES;                     // 190,864
+static constexpr uint32_t kEnumH9Off = kEnumHistOff + kHistBinsPad * 4;       // 220,720
+static constexpr uint32_t kEnumBarOff = kEnumH9Off + 9 * 8;                   // 220,792
+static constexpr uint32_t kEnumBinOff = kEnumBarOff + 16;                      // u32[8][64]: C(v, k) at [k*64 + v]
+static constexpr uint32_t kSmemEnum = kEnumBinOff + 8 * 64 * 4;
 static constexpr uint32_t kSmemTabOnly = kSmemTab + 16;
 
 // ------------------------------------------------------------------------------------------------
 // table staging: one TMA bulk copy of the whole image, completion on an mbarrier
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_tables(unsigned char* s_tab, const uint16_t* __restrict__ g_tab, uint64_t* s_bar)
+__device__ __forceinline__ void stage_image(unsigned char* s_dst, const void* __restrict__ g_src, uint32_t bytes, uint64_t* s_bar)
 {
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_bar);
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_tab);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_dst);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -47,13 +52,14 @@ __device__ __forceinline__ void stage_tables(unsigned char* s_tab, const uint16_
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TAB_BYTES) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         constexpr uint32_t kChunk = 32768;
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(g_tab);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(g_src);
 #pragma unroll 1
-        for (uint32_t off = 0; off < TAB_BYTES; off += kChunk) {
+        for (uint32_t off = 0; off < bytes; off += kChunk) {
+            const uint32_t n = bytes - off < kChunk ? bytes - off : kChunk;   // multiples of 16
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
-                         "l"(src + off), "r"(kChunk), "r"(bar)
+                         "l"(src + off), "r"(n), "r"(bar)
                          : "memory");
         }
     }
@@ -67,6 +73,28 @@ __device__ __forceinline__ void stage_tables(unsigned char* s_tab, const uint16_
             : "r"(bar), "r"(0u)
             : "memory");
     }
+}
+
+__device__ __forceinline__ void stage_tables(unsigned char* s_tab, const uint16_t* __restrict__ g_tab, uint64_t* s_bar)
+{
+    stage_image(s_tab, g_tab, TAB_BYTES, s_bar);
+}
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a)
+{
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void red_inc_shared(uint32_t a)
+{
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory");
 }
 
 __device__ __forceinline__ uint64_t ld_nc_u64(const uint64_t* p)
@@ -133,65 +161,129 @@ k_eval7_gmem(const uint16_t* __restrict__ g_tab, const void* __restrict__ hands,
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: exhaustive C(52,7) over a colex index range
+// K2: exhaustive C(52,7) over a colex index range (arithmetic and table layout: phe_enum.cuh).
+// A warp walks tiles of consecutive colex hand indices block by block: a block is one (c3..c6) suffix whose
+// C(c3,3) triples are consecutive hand indices; the 32 lanes stride over the triples.  Everything outside
+// the triple loop is warp-uniform; the only divergent code is the flush path (3 % of hands).
 // ------------------------------------------------------------------------------------------------
+// FLUSH-table address of the hand (block s3, triple t) whose flush suit is flagged in x (one bit of 0x8888)
+__device__ __forceinline__ uint32_t enum_flush_addr(uint32_t x, uint32_t t, uint32_t s3lo, uint32_t s3hi, uint32_t a_fl,
+                                                    const uint64_t* __restrict__ g_trimask)
+{
+    const uint2 m = __ldg(reinterpret_cast<const uint2*>(g_trimask) + t);
+    const uint32_t s = (31u - (uint32_t)__clz(x)) >> 2;          // suit 0..3 from the flagged nibble
+    const uint32_t sel = s * 0x22u + 0x10u;                      // PRMT selector: bytes 2s and 2s+1 of {hi:lo}
+    const uint32_t suit_lane = __byte_perm(s3lo | m.x, s3hi | m.y, sel) & 0x1FFFu;
+    return a_fl + 2u * suit_lane;
+}
+
 __global__ void __launch_bounds__(kCtaThreads, 1)
-k_enum7(const uint16_t* __restrict__ g_tab, unsigned long long* __restrict__ hist9, unsigned long long* __restrict__ hist7463,
-        uint64_t begin, uint64_t end)
+k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_trimask, unsigned long long* __restrict__ hist9,
+        unsigned long long* __restrict__ hist7463, uint64_t begin, uint64_t end, uint32_t tile_size, unsigned int* __restrict__ tile_counter)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + kSmemTab);
-    unsigned long long* s_h9 = reinterpret_cast<unsigned long long*>(smem + kSmemTab + kHistBinsPad * 4);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_h9 + 9);
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + kEnumHistOff);
+    unsigned long long* s_h9 = reinterpret_cast<unsigned long long*>(smem + kEnumH9Off);
     for (int i = threadIdx.x; i < kHistBinsPad; i += blockDim.x) s_hist[i] = 0;
     if (threadIdx.x < 9) s_h9[threadIdx.x] = 0;
-    stage_tables(smem, g_tab, s_bar);   // contains a __syncthreads after the zeroing stores
+    uint32_t* s_bin = reinterpret_cast<uint32_t*>(smem + kEnumBinOff);
+    if (threadIdx.x < 512) {
+        const int k = threadIdx.x >> 6, v = threadIdx.x & 63;
+        s_bin[threadIdx.x] = v <= 52 ? c_binom[v * 8 + k] : 0xFFFFFFFFu;
+    }
+    stage_image(smem, g_img, ENUM_IMG_BYTES, reinterpret_cast<uint64_t*>(smem + kEnumBarOff));
     __syncthreads();
-    const SharedTab tab{(uint32_t)__cvta_generic_to_shared(smem)};
-    const HashParams hp = c_hp;
 
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t a_tri = sb + EOFF_TRI, a_ms = sb + EOFF_MSRANK, a_fl = sb + EOFF_FLUSH, a_hist = sb + kEnumHistOff;
+    const uint32_t lane = threadIdx.x & 31;
+    const Binom C{c_binom};
+
+    // Dynamic tile scheduling: tiles of `tile_size` consecutive colex indices are handed out through an atomic
+    // counter in increasing order.  Low indices hold the short blocks (small c3: few triples per block, poor lane
+    // use), i.e. the expensive tiles go first and the cheap ones level the finish line.
     const uint64_t total = end - begin;
-    const uint64_t nthr = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t per = (total + nthr - 1) / nthr;
-    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t my_b = begin + gtid * per;
-    uint64_t my_e = my_b + per;
-    if (my_e > end) my_e = end;
-    if (my_b < my_e) {
+    const uint32_t ntiles = (uint32_t)((total + tile_size - 1) / tile_size);
+    const uint32_t a_bin = sb + kEnumBinOff;
+    for (;;) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(tile_counter, 1u);
+        tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+        if (tile >= ntiles) break;
+        const uint64_t wb = begin + (uint64_t)tile * tile_size;
+        uint64_t we = wb + tile_size;
+        if (we > end) we = end;
+        // warp-cooperative colex unrank: lane v (and v + 32) tests C(v, k) <= rem; the count of hits - 1 is c_i
         int c[7];
-        colex_unrank7(my_b, Binom{c_binom}, c);
-        int c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4], c5 = c[5], c6 = c[6];
-        uint64_t s2 = id_bit(c2) | id_bit(c3) | id_bit(c4) | id_bit(c5) | id_bit(c6);
-        uint64_t s1 = s2 | id_bit(c1);
-        const uint32_t n = (uint32_t)(my_e - my_b);
-#pragma unroll 1
-        for (uint32_t it = 0; it < n; ++it) {
-            const uint32_t r = eval7(s1 | id_bit(c0), tab, hp);
-            atomicAdd(&s_hist[r], 1u);
-            // colex successor: smallest element runs fastest
-            ++c0;
-            if (c0 == c1) {
-                c0 = 0; ++c1;
-                if (c1 == c2) {
-                    c1 = 1; ++c2;
-                    if (c2 == c3) {
-                        c2 = 2; ++c3;
-                        if (c3 == c4) {
-                            c3 = 3; ++c4;
-                            if (c4 == c5) {
-                                c4 = 4; ++c5;
-                                if (c5 == c6) { c5 = 5; ++c6; }
-                            }
-                        }
-                    }
-                    s2 = id_bit(c2) | id_bit(c3) | id_bit(c4) | id_bit(c5) | id_bit(c6);
-                }
-                s1 = s2 | id_bit(c1);
+        {
+            uint32_t rem = (uint32_t)wb;
+#pragma unroll
+            for (int i = 6; i >= 0; i--) {
+                const uint32_t b0 = lds_u32(a_bin + 4u * ((uint32_t)(i + 1) * 64u + lane));
+                const uint32_t b1 = lds_u32(a_bin + 4u * ((uint32_t)(i + 1) * 64u + lane + 32u));
+                const int hits = __popc(__ballot_sync(0xFFFFFFFFu, b0 <= rem)) + __popc(__ballot_sync(0xFFFFFFFFu, lane + 32u <= 51u && b1 <= rem));
+                c[i] = hits - 1;
+                rem -= lds_u32(a_bin + 4u * ((uint32_t)(i + 1) * 64u + (uint32_t)c[i]));
             }
+        }
+        int c3 = c[3], c4 = c[4], c5 = c[5], c6 = c[6];
+        uint64_t remaining = we - wb;
+        uint32_t t_start = C(c[2], 3) + C(c[1], 2) + (uint32_t)c[0];
+        for (;;) {
+            EnumBlock b;
+            enum_block_setup(c3, c4, c5, c6, C, b);
+            uint32_t stop = b.ntriples;
+            if ((uint64_t)stop > (uint64_t)t_start + remaining) stop = (uint32_t)(t_start + remaining);
+            const uint32_t msb = a_ms + 2u * b.bidx3;
+            const uint32_t s3lo = (uint32_t)b.s3, s3hi = (uint32_t)(b.s3 >> 32), kbias = b.kbias;
+            // warp-uniform trip counts; kU hands per lane per trip keep kU independent LDS -> (LDG) -> LDS -> ATOMS
+            // chains in flight, which is what hides the L2 round trip of the flush path
+            constexpr int kU = 4;
+            uint32_t tb = t_start;
+            for (; tb + 32 * kU <= stop; tb += 32 * kU) {
+                const uint32_t t0 = tb + lane;
+                uint32_t e[kU], a[kU], x[kU], any = 0;
+#pragma unroll
+                for (int u = 0; u < kU; u++) e[u] = lds_u32(a_tri + 4u * t0 + 128u * u);
+#pragma unroll
+                for (int u = 0; u < kU; u++) {
+                    a[u] = msb + (e[u] >> 16);
+                    x[u] = (e[u] + kbias) & 0x8888u;
+                    any |= x[u];
+                }
+                if (__any_sync(0xFFFFFFFFu, any != 0u)) {   // some lane holds a flush (3 % of hands)
+#pragma unroll
+                    for (int u = 0; u < kU; u++)
+                        if (x[u]) a[u] = enum_flush_addr(x[u], t0 + 32u * u, s3lo, s3hi, a_fl, g_trimask);
+                }
+                uint32_t r[kU];
+#pragma unroll
+                for (int u = 0; u < kU; u++) r[u] = lds_u16(a[u]);
+#pragma unroll
+                for (int u = 0; u < kU; u++) red_inc_shared(a_hist + 4u * r[u]);
+            }
+            for (; tb < stop; tb += 32) {   // at most kU partial trips
+                const uint32_t t0 = tb + lane;
+                if (t0 < stop) {
+                    const uint32_t e0 = lds_u32(a_tri + 4u * t0);
+                    uint32_t a0 = msb + (e0 >> 16);
+                    const uint32_t x0 = (e0 + kbias) & 0x8888u;
+                    if (x0) a0 = enum_flush_addr(x0, t0, s3lo, s3hi, a_fl, g_trimask);
+                    red_inc_shared(a_hist + 4u * lds_u16(a0));
+                }
+            }
+            remaining -= stop - t_start;
+            if (!remaining) break;
+            t_start = 0;
+            enum_block_next(c3, c4, c5, c6);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kHistBins; i += blockDim.x) {
+    // flush: every CTA starts at a different bin so the 64-bit REDs do not pile up on one L2 line
+    const int rot = (int)((blockIdx.x * 397u) % (uint32_t)kHistBins);
+    for (int k = threadIdx.x; k < kHistBins; k += blockDim.x) {
+        int i = k + rot;
+        if (i >= kHistBins) i -= kHistBins;
         const uint32_t v = s_hist[i];
         if (v) {
             if (hist7463) atomicAdd(hist7463 + i, (unsigned long long)v);
@@ -400,11 +492,16 @@ k_deal(const uint64_t* __restrict__ known, int64_t n, int need, uint64_t seed, u
 namespace {
 
 constexpr int kMaxDevices = 64;
+constexpr uint32_t kCounterRing = 256;
 
 struct DevCtx {
     std::once_flag once;
     int status = PHE_ENODEVICE;
     uint16_t* d_image = nullptr;
+    unsigned char* d_enum = nullptr;
+    uint64_t* d_trimask = nullptr;
+    unsigned int* d_counters = nullptr;   // ring of tile counters, one per in-flight enumeration launch
+    std::atomic<uint32_t> next_counter{0};
     int sm_count = 0;
 };
 
@@ -414,6 +511,8 @@ thread_local char t_cuda_err[256] = "";
 
 std::once_flag g_image_once;
 std::vector<uint16_t> g_image;
+std::vector<unsigned char> g_enum_image;
+std::vector<uint64_t> g_trimask;
 HashParams g_hp;
 uint32_t g_binom[53 * 8];
 bool g_image_ok = false;
@@ -436,6 +535,9 @@ void init_device(int device)
     std::call_once(g_image_once, [] {
         g_image.resize(TAB_U16);
         g_image_ok = build_table_image(g_image.data(), &g_hp);
+        g_enum_image.resize(ENUM_IMG_BYTES);
+        g_trimask.resize(N_TRIPLES);
+        g_image_ok = g_image_ok && build_enum_image(g_enum_image.data(), g_trimask.data());
         build_binom(g_binom);
     });
     if (!g_image_ok) { cx.status = PHE_EINVAL; return; }
@@ -455,6 +557,11 @@ void init_device(int device)
     chk(cudaSetDevice(device), "cudaSetDevice");
     chk(cudaMalloc(&cx.d_image, TAB_BYTES), "cudaMalloc(tables)");
     chk(cudaMemcpy(cx.d_image, g_image.data(), TAB_BYTES, cudaMemcpyHostToDevice), "cudaMemcpy(tables)");
+    chk(cudaMalloc(&cx.d_enum, ENUM_IMG_BYTES), "cudaMalloc(enum tables)");
+    chk(cudaMemcpy(cx.d_enum, g_enum_image.data(), ENUM_IMG_BYTES, cudaMemcpyHostToDevice), "cudaMemcpy(enum tables)");
+    chk(cudaMalloc(&cx.d_trimask, TRIMASK_BYTES), "cudaMalloc(trimask)");
+    chk(cudaMemcpy(cx.d_trimask, g_trimask.data(), TRIMASK_BYTES, cudaMemcpyHostToDevice), "cudaMemcpy(trimask)");
+    chk(cudaMalloc(&cx.d_counters, kCounterRing * sizeof(unsigned int)), "cudaMalloc(counters)");
     chk(cudaMemcpyToSymbol(c_hp, &g_hp, sizeof g_hp), "cudaMemcpyToSymbol(c_hp)");
     chk(cudaMemcpyToSymbol(c_binom, g_binom, sizeof g_binom), "cudaMemcpyToSymbol(c_binom)");
     chk(cudaFuncSetAttribute(k_eval7_smem<PHE_LAYOUT_IDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr eval7 ids");
@@ -503,7 +610,7 @@ struct Scratch {
         return PHE_OK;
     }
 };
-thread_local Scratch t_in, t_out, t_aux;
+thread_local Scratch t_in, t_out;
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -588,8 +695,15 @@ int phe_enum7(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin, uint64_t
     const uint64_t total = comb_end - comb_begin;
     uint64_t ctas = (total + kCtaThreads * 64 - 1) / (kCtaThreads * 64);
     if (ctas > (uint64_t)cx->sm_count) ctas = cx->sm_count;
-    k_enum7<<<(unsigned)ctas, kCtaThreads, kSmemEnum, static_cast<cudaStream_t>(stream)>>>(
-        cx->d_image, reinterpret_cast<unsigned long long*>(hist9), reinterpret_cast<unsigned long long*>(hist7463), comb_begin, comb_end);
+    // ~24 tiles per resident warp, at least 256 hands each
+    uint64_t tile = total / (ctas * (kCtaThreads / 32) * 24);
+    if (tile < 256) tile = 256;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned int* counter = cx->d_counters + (cx->next_counter.fetch_add(1, std::memory_order_relaxed) % kCounterRing);
+    PHE_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    k_enum7<<<(unsigned)ctas, kCtaThreads, kSmemEnum, st>>>(
+        cx->d_enum, cx->d_trimask, reinterpret_cast<unsigned long long*>(hist9), reinterpret_cast<unsigned long long*>(hist7463), comb_begin, comb_end,
+        (uint32_t)tile, counter);
     return after_launch("enum7 launch");
 }
 

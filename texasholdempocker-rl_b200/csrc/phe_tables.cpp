@@ -10,6 +10,7 @@
 //   NOFLUSH is addressed by a two-level perfect hash (hash-and-displace) of the bit-sliced rank
 //   multiplicities (b0, b1, b2) the evaluator derives from a card-set word.
 #include "phe_tables.h"
+#include "phe_enum.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -245,6 +246,48 @@ bool build_table_image(uint16_t* image, HashParams* hp_out)
         if (try_build(keys, hp, image)) { *hp_out = hp; return true; }
     }
     return false;
+}
+
+// ---- enumeration image (phe_enum.cuh) --------------------------------------------------------
+static void fill_msrank(uint8_t cnt[13], int rank_from, int placed, uint32_t idx, uint16_t* ms)
+{
+    // places cards in non-decreasing rank order; idx accumulates C(r + i - 1, i) for the i-th card
+    if (placed == 7) {
+        bool ok = true;
+        for (int r = 0; r < 13; r++) ok = ok && cnt[r] <= 4;
+        ms[idx] = ok ? noflush_rank(cnt) : (uint16_t)0;
+        return;
+    }
+    for (int r = rank_from; r < 13; r++) {
+        cnt[r]++;
+        fill_msrank(cnt, r, placed + 1, idx + binom_u32(r + placed, placed + 1), ms);
+        cnt[r]--;
+    }
+}
+
+bool build_enum_image(unsigned char* image, uint64_t* trimask)
+{
+    std::memset(image, 0, ENUM_IMG_BYTES);
+    uint16_t* ms = reinterpret_cast<uint16_t*>(image + EOFF_MSRANK);
+    uint8_t cnt[13] = {0};
+    fill_msrank(cnt, 0, 0, 0, ms);
+    uint16_t* fl = reinterpret_cast<uint16_t*>(image + EOFF_FLUSH);
+    for (uint32_t m = 0; m < FLUSH_SIZE; m++) {
+        const int pc = __builtin_popcount(m);
+        fl[m] = (pc >= 5 && pc <= 7) ? flush_rank(m) : (uint16_t)0;
+    }
+    uint32_t* tri = reinterpret_cast<uint32_t*>(image + EOFF_TRI);
+    for (int c2 = 2; c2 < 49; c2++)
+        for (int c1 = 1; c1 < c2; c1++)
+            for (int c0 = 0; c0 < c1; c0++) {
+                const uint32_t t = binom_u32(c2, 3) + binom_u32(c1, 2) + (uint32_t)c0;
+                const uint32_t r0 = c0 >> 2, r1 = c1 >> 2, r2 = c2 >> 2;
+                const uint32_t part = binom_u32(r0, 1) + binom_u32(r1 + 1, 2) + binom_u32(r2 + 2, 3);
+                const uint32_t suits = (1u << (4 * (c0 & 3))) + (1u << (4 * (c1 & 3))) + (1u << (4 * (c2 & 3)));
+                tri[t] = ((2u * part) << 16) | suits;
+                trimask[t] = id_bit(c0) | id_bit(c1) | id_bit(c2);
+            }
+    return true;
 }
 
 }  // namespace phe

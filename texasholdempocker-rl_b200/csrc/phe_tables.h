@@ -22,4 +22,7 @@ std::vector<NoflushKey> all_noflush_keys();
 // fills image[TAB_U16] and the hash multipliers; false if no perfect hash was found
 bool build_table_image(uint16_t* image, HashParams* hp_out);
 
+// fills image[ENUM_IMG_BYTES] and trimask[N_TRIPLES] (layouts in phe_enum.cuh)
+bool build_enum_image(unsigned char* image, uint64_t* trimask);
+
 }  // namespace phe
