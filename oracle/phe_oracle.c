@@ -420,35 +420,14 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 }
 
 /* The dealing stream the CUDA kernels use (DESIGN.md "RNG stream"):
- *   key     = (seed lo32, seed hi32)
- *   counter = (sample lo32, sample hi32, stream id, block number)
- *   each 32-bit output word yields five 6-bit draws, least significant first
- *   (bits 30-31 unused); a draw x addresses bit x of the 64-bit card-set word
- *   (bit 16*suit + rank); it is accepted iff that bit is clear in `used`, which
- *   starts as known cards | the twelve non-card bits (rank nibble 13..15).
- *   Accepted cards fill, in order: the missing board cards, then two hole
- *   cards per opponent. */
-typedef struct { uint32_t ctr[4], key[2], out[4]; int word, chunk; } deal_rng;
-
-static void rng_start(deal_rng *g, uint64_t seed, uint64_t sample, uint32_t stream)
-{
-    g->key[0] = (uint32_t)seed; g->key[1] = (uint32_t)(seed >> 32);
-    g->ctr[0] = (uint32_t)sample; g->ctr[1] = (uint32_t)(sample >> 32);
-    g->ctr[2] = stream; g->ctr[3] = 0;
-    orc_philox4x32_10(g->ctr, g->key, g->out);
-    g->word = 0; g->chunk = 0;
-}
-
-static int rng_draw6(deal_rng *g)
-{
-    if (g->chunk == 5) { g->chunk = 0; g->word++; }
-    if (g->word == 4) { g->word = 0; g->ctr[3]++; orc_philox4x32_10(g->ctr, g->key, g->out); }
-    int x = (int)((g->out[g->word] >> (6 * g->chunk)) & 63u);
-    g->chunk++;
-    return x;
-}
-
-#define NONCARD_BITS 0xE000E000E000E000ull
+ *   Philox block b = philox4x32_10(counter = (sample lo32, sample hi32, stream id, b), key = (seed lo32, seed hi32)).
+ *   Every 32-bit output word w (words 0..3 of block 0, then block 1, ...) carries five draws:
+ *     suit_j = (w >> 2j) & 3 (low ten bits), rank_j = j-th base-13 digit of v = w >> 10, least significant first;
+ *     a word with v >= 11 * 13^5 is skipped whole, so that the five digits are exactly uniform.
+ *   Draw j addresses bit 16*suit_j + rank_j of the 64-bit card-set word and is accepted iff that bit is clear in
+ *   `used` (initially the known cards); accepted cards fill, in order, the missing board cards and then two
+ *   hole cards per opponent.  Words are consumed until enough cards are accepted. */
+#define DEAL_V_LIMIT (11u * 371293u)
 
 static inline uint8_t bit_to_id(int b) { return (uint8_t)((b & 15) * 4 + (b >> 4)); }
 static inline int id_to_bit(int id) { return 16 * (id & 3) + (id >> 2); }
@@ -463,14 +442,26 @@ static int mask_to_ids(uint64_t m, uint8_t *out, int cap)
 /* deal `need` cards with the shared stream; returns them as bit positions */
 static void deal_shared(uint64_t known, uint64_t seed, uint64_t sample, uint32_t stream, int need, int *bits)
 {
-    deal_rng g; rng_start(&g, seed, sample, stream);
-    uint64_t used = known | NONCARD_BITS;
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t ctr[4] = {(uint32_t)sample, (uint32_t)(sample >> 32), stream, 0};
+    uint64_t used = known;
     int got = 0;
     while (got < need) {
-        int x = rng_draw6(&g);
-        if (used >> x & 1) continue;
-        used |= 1ull << x;
-        bits[got++] = x;
+        uint32_t out[4];
+        orc_philox4x32_10(ctr, key, out);
+        ctr[3]++;
+        for (int wi = 0; wi < 4 && got < need; wi++) {
+            uint32_t w = out[wi], v = w >> 10;
+            if (v >= DEAL_V_LIMIT) continue;
+            for (int j = 0; j < 5 && got < need; j++) {
+                int rank = (int)(v % 13u), suit = (int)((w >> (2 * j)) & 3u);
+                v /= 13u;
+                int pos = 16 * suit + rank;
+                if (used >> pos & 1) continue;
+                used |= 1ull << pos;
+                bits[got++] = pos;
+            }
+        }
     }
 }
 

@@ -143,71 +143,69 @@ PHE_UNROLL
 }
 
 // ---- dealing -----------------------------------------------------------------------------------
-// Draws `need` (<= 21) distinct cards outside `known` for (seed, stream, sample).  Six-bit draws,
-// five per Philox word, least significant first; a draw is accepted iff its bit is clear in the
-// running used set (known | the twelve non-card bits).  The accepted positions are shifted into a
-// 128-bit register: the i-th accepted card ends at bits [6*(need-1-i), +6).
+// Draws `need` (<= 21) distinct cards outside `known` for (seed, stream, sample); exactly uniform over the
+// unknown cards, a pure function of its arguments.  Philox block b = philox(counter (sample lo, sample hi,
+// stream, b), key seed).  Every 32-bit output word w (words 0..3 of block 0, then block 1, ...) carries five
+// draws: suit_j = (w >> 2j) & 3 from the low ten bits, and v = w >> 10 gives rank_j as the base-13 digits of v,
+// least significant first.  A word with v >= 11 * 13^5 is skipped whole (2.6 %), which makes the digits exactly
+// uniform.  Draw j addresses card-set bit 16*suit_j + rank_j and is accepted iff that bit is clear in the running
+// used set; accepted positions are stored in order.  Words are consumed until `need` cards are accepted.
 constexpr int MAX_DEAL = 21;
+constexpr uint32_t DEAL_V_LIMIT = 11u * 371293u;   // 11 * 13^5 = 4,084,223 <= 2^22
 
-struct Dealt {
-    uint32_t w0, w1, w2, w3;
-    PHE_HD uint32_t get(int i, int need) const   // i-th accepted card's bit position
-    {
-        const int sh = 6 * (need - 1 - i);
-        const int word = sh >> 5, off = sh & 31;
-        const uint32_t a = word == 0 ? w0 : (word == 1 ? w1 : (word == 2 ? w2 : w3));
-        const uint32_t b = word == 0 ? w1 : (word == 1 ? w2 : (word == 2 ? w3 : 0u));
-        const uint64_t v = ((uint64_t)b << 32) | a;
-        return (uint32_t)(v >> off) & 63u;
-    }
+struct LocalCards {          // host / small kernels: accepted positions in a thread-local array
+    uint8_t p[MAX_DEAL];
+    PHE_HD void put(int k, uint32_t pos) { p[k] = (uint8_t)pos; }
+    PHE_HD uint32_t get(int k) const { return p[k]; }
 };
 
-PHE_HD Dealt deal_cards(uint64_t known, uint64_t seed, uint64_t sample, uint32_t stream, int need)
+template <class Cards>
+PHE_HD void deal_cards(uint64_t known, uint64_t seed, uint64_t sample, uint32_t stream, int need, Cards& out)
 {
-    uint32_t used_lo = (uint32_t)(known | NONCARD_BITS), used_hi = (uint32_t)((known | NONCARD_BITS) >> 32);
-    Dealt dl; dl.w0 = dl.w1 = dl.w2 = dl.w3 = 0;
+    uint32_t used_lo = (uint32_t)known, used_hi = (uint32_t)(known >> 32);
     int got = 0;
     for (uint32_t blk = 0; got < need; blk++) {
         uint32_t rnd[4];
         philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), stream, blk, (uint32_t)seed, (uint32_t)(seed >> 32), rnd);
 PHE_UNROLL
         for (int wi = 0; wi < 4; wi++) {
-            uint32_t w = rnd[wi];
+            if (got >= need) break;
+            const uint32_t w = rnd[wi];
+            uint32_t v = w >> 10;
+            if (v >= DEAL_V_LIMIT) continue;
 PHE_UNROLL
-            for (int ch = 0; ch < 5; ch++) {
-                const uint32_t x = w & 63u;
-                w >>= 6;
-                const uint32_t word = (x & 32u) ? used_hi : used_lo;
-                const uint32_t bit = 1u << (x & 31u);
+            for (int j = 0; j < 5; j++) {
+                const uint32_t q = v / 13u;
+                const uint32_t rank = v - q * 13u;
+                v = q;
+                const uint32_t suit = (w >> (2 * j)) & 3u;
+                const uint32_t bit = 1u << (((suit & 1u) << 4) | rank);
+                const uint32_t word = (suit & 2u) ? used_hi : used_lo;
                 if (!(word & bit) && got < need) {
-                    if (x & 32u) used_hi |= bit; else used_lo |= bit;
-                    dl.w3 = (dl.w3 << 6) | (dl.w2 >> 26);
-                    dl.w2 = (dl.w2 << 6) | (dl.w1 >> 26);
-                    dl.w1 = (dl.w1 << 6) | (dl.w0 >> 26);
-                    dl.w0 = (dl.w0 << 6) | x;
+                    if (suit & 2u) used_hi |= bit; else used_lo |= bit;
+                    out.put(got, (suit << 4) | rank);
                     got++;
                 }
             }
         }
     }
-    return dl;
 }
 
 // one Monte-Carlo rollout (env/workflow.py:130-148 generalised to n_opp opponents):
-// returns 0 win, 1 tie, 2 loss for the hero
-template <class Tab>
+// returns 0 win, 1 tie, 2 loss for the hero.  `cards` is scratch for the dealt positions.
+template <class Tab, class Cards>
 PHE_HD int mc_rollout(const Tab& tab, const HashParams& hp, uint64_t known, uint64_t hero, int nboard, int n_opp,
-                      uint64_t seed, uint64_t sample, uint32_t stream)
+                      uint64_t seed, uint64_t sample, uint32_t stream, Cards& cards)
 {
     const int need = (5 - nboard) + 2 * n_opp;
-    const Dealt dl = deal_cards(known, seed, sample, stream, need);
+    deal_cards(known, seed, sample, stream, need, cards);
     uint64_t board = known & ~hero;
     int k = 0;
-    for (; k < 5 - nboard; k++) board |= pos_bit(dl.get(k, need));
+    for (; k < 5 - nboard; k++) board |= pos_bit(cards.get(k));
     const uint32_t hr = eval7(board | hero, tab, hp);
     uint32_t best = 0xFFFFu;
     for (int o = 0; o < n_opp; o++) {
-        const uint64_t hole = pos_bit(dl.get(k, need)) | pos_bit(dl.get(k + 1, need));
+        const uint64_t hole = pos_bit(cards.get(k)) | pos_bit(cards.get(k + 1));
         k += 2;
         const uint32_t r = eval7(board | hole, tab, hp);
         best = r < best ? r : best;

@@ -50,8 +50,9 @@ void hc_eval7_masks(const uint64_t* m, int64_t n, uint16_t* out)
 
 void hc_deal(uint64_t known, uint64_t seed, uint64_t sample, uint32_t stream, int need, uint8_t* ids)
 {
-    const Dealt d = deal_cards(known, seed, sample, stream, need);
-    for (int i = 0; i < need; i++) ids[i] = (uint8_t)pos_to_id(d.get(i, need));
+    LocalCards d;
+    deal_cards(known, seed, sample, stream, need, d);
+    for (int i = 0; i < need; i++) ids[i] = (uint8_t)pos_to_id(d.get(i));
 }
 
 void hc_equity_mc(uint64_t known, uint64_t hero, int n_opp, uint64_t rollouts, uint64_t offset, uint64_t seed,
@@ -59,7 +60,8 @@ void hc_equity_mc(uint64_t known, uint64_t hero, int n_opp, uint64_t rollouts, u
 {
     GlobalTab tab{g_image.data()};
     const int nboard = __builtin_popcountll(known & ~hero);
-    for (uint64_t s = 0; s < rollouts; s++) wtl[mc_rollout(tab, g_hp, known, hero, nboard, n_opp, seed, offset + s, stream)]++;
+    LocalCards scratch;
+    for (uint64_t s = 0; s < rollouts; s++) wtl[mc_rollout(tab, g_hp, known, hero, nboard, n_opp, seed, offset + s, stream, scratch)]++;
 }
 
 void hc_colex_unrank7(uint64_t idx, int32_t* c)
@@ -91,8 +93,9 @@ int hc_equity_plan(const uint8_t* exist, int n_exist, const int32_t* plan, int n
             uint64_t kn = known;
             for (int i = pd.n_exist; i < base; i++) kn |= id_bit(cards[i]);
             for (int j = 0; j < pd.rnd_n; j++) {
-                const Dealt d = deal_cards(kn, seed, leaf * (uint64_t)pd.rnd_n + (uint64_t)j, stream, pd.rnd_k);
-                for (int i = 0; i < pd.rnd_k; i++) cards[base + i] = (uint8_t)pos_to_id(d.get(i, pd.rnd_k));
+                LocalCards d;
+                deal_cards(kn, seed, leaf * (uint64_t)pd.rnd_n + (uint64_t)j, stream, pd.rnd_k, d);
+                for (int i = 0; i < pd.rnd_k; i++) cards[base + i] = (uint8_t)pos_to_id(d.get(i));
                 out[plan_leaf_result(tab, g_hp, cards)]++; out[3]++;
             }
         }

@@ -37,6 +37,7 @@ static constexpr uint32_t kEnumBarOff = kEnumH9Off + 9 * 8;                   //
 static constexpr uint32_t kEnumBinOff = kEnumBarOff + 16;                      // u32[8][64]: C(v, k) at [k*64 + v]
 static constexpr uint32_t kSmemEnum = kEnumBinOff + 8 * 64 * 4;
 static constexpr uint32_t kSmemTabOnly = kSmemTab + 16;
+static constexpr uint32_t kSmemMc = kSmemTabOnly + MAX_DEAL * kCtaThreads;    // + one byte column per thread for dealt cards
 
 // ------------------------------------------------------------------------------------------------
 // table staging: one TMA bulk copy of the whole image, completion on an mbarrier
@@ -295,13 +296,28 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
 }
 
 // ------------------------------------------------------------------------------------------------
+// dealt-card scratch of the Monte-Carlo kernels: row k of a [MAX_DEAL][blockDim] byte matrix in shared memory
+// (threads of a warp touch 32 consecutive bytes of one row: conflict free)
+struct SmemCards {
+    uint32_t base;     // shared address of this thread's column
+    uint32_t stride;   // blockDim.x
+    __device__ __forceinline__ void put(int k, uint32_t pos) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(base + (uint32_t)k * stride), "r"(pos) : "memory"); }
+    __device__ __forceinline__ uint32_t get(int k) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)k * stride) : "memory");
+        return v;
+    }
+};
+
 // K3: Monte-Carlo equity.  One warp works on one (state, sample chunk) item at a time; lanes take
 // samples chunk_begin + lane + 32 i.  The deal is a pure function of the global sample index.
 // ------------------------------------------------------------------------------------------------
 template <class Tab>
 __device__ __forceinline__ void equity_mc_body(const Tab& tab, const ulonglong2* __restrict__ states, int64_t n_states,
                                                int n_opp_default, uint64_t rollouts, uint64_t sample_offset, uint64_t seed,
-                                               uint32_t state_base, unsigned long long* __restrict__ wtl, uint32_t chunk)
+                                               uint32_t state_base, unsigned long long* __restrict__ wtl, uint32_t chunk,
+                                               SmemCards cards)
 {
     const HashParams hp = c_hp;
     const uint32_t lane = threadIdx.x & 31;
@@ -321,7 +337,7 @@ __device__ __forceinline__ void equity_mc_body(const Tab& tab, const ulonglong2*
         if (e > rollouts) e = rollouts;
         uint32_t w = 0, t = 0, l = 0;
         for (uint64_t i = b + lane; i < e; i += 32) {
-            const int res = mc_rollout(tab, hp, known, hero, nboard, n_opp, seed, sample_offset + i, state_base + (uint32_t)s);
+            const int res = mc_rollout(tab, hp, known, hero, nboard, n_opp, seed, sample_offset + i, state_base + (uint32_t)s, cards);
             w += (res == 0); t += (res == 1); l += (res == 2);
         }
         w = __reduce_add_sync(0xFFFFFFFFu, w);
@@ -343,7 +359,8 @@ k_equity_mc_smem(const uint16_t* __restrict__ g_tab, const ulonglong2* __restric
     extern __shared__ __align__(128) unsigned char smem[];
     stage_tables(smem, g_tab, reinterpret_cast<uint64_t*>(smem + kSmemTab));
     const SharedTab tab{(uint32_t)__cvta_generic_to_shared(smem)};
-    equity_mc_body(tab, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk);
+    const SmemCards cards{(uint32_t)__cvta_generic_to_shared(smem) + kSmemTabOnly + threadIdx.x, blockDim.x};
+    equity_mc_body(tab, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk, cards);
 }
 
 __global__ void __launch_bounds__(256)
@@ -351,8 +368,10 @@ k_equity_mc_gmem(const uint16_t* __restrict__ g_tab, const ulonglong2* __restric
                  uint64_t rollouts, uint64_t sample_offset, uint64_t seed, uint32_t state_base,
                  unsigned long long* __restrict__ wtl, uint32_t chunk)
 {
+    __shared__ unsigned char s_cards[MAX_DEAL * 256];
     const GlobalTab tab{g_tab};
-    equity_mc_body(tab, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk);
+    const SmemCards cards{(uint32_t)__cvta_generic_to_shared(s_cards) + threadIdx.x, blockDim.x};
+    equity_mc_body(tab, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk, cards);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -384,8 +403,9 @@ __device__ __forceinline__ void equity_plan_body(const Tab& tab, const uint8_t* 
         } else {
             for (int i = pd.n_exist; i < base; i++) known |= id_bit(cards[i]);
             for (int j = 0; j < pd.rnd_n; j++) {
-                const Dealt d = deal_cards(known, seed, leaf * (uint64_t)pd.rnd_n + (uint64_t)j, stream_base + (uint32_t)task, pd.rnd_k);
-                for (int i = 0; i < pd.rnd_k; i++) cards[base + i] = (uint8_t)pos_to_id(d.get(i, pd.rnd_k));
+                LocalCards d;
+                deal_cards(known, seed, leaf * (uint64_t)pd.rnd_n + (uint64_t)j, stream_base + (uint32_t)task, pd.rnd_k, d);
+                for (int i = 0; i < pd.rnd_k; i++) cards[base + i] = (uint8_t)pos_to_id(d.get(i));
                 const int res = plan_leaf_result(tab, hp, cards);
                 w += (res == 0); t += (res == 1); l += (res == 2);
             }
@@ -482,8 +502,9 @@ k_deal(const uint64_t* __restrict__ known, int64_t n, int need, uint64_t seed, u
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const Dealt d = deal_cards(known[i] & CARD_BITS, seed, sample, stream_base + (uint32_t)i, need);
-    for (int k = 0; k < need; k++) cards_out[i * need + k] = (uint8_t)pos_to_id(d.get(k, need));
+    LocalCards d;
+    deal_cards(known[i] & CARD_BITS, seed, sample, stream_base + (uint32_t)i, need, d);
+    for (int k = 0; k < need; k++) cards_out[i * need + k] = (uint8_t)pos_to_id(d.get(k));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -567,7 +588,7 @@ void init_device(int device)
     chk(cudaFuncSetAttribute(k_eval7_smem<PHE_LAYOUT_IDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr eval7 ids");
     chk(cudaFuncSetAttribute(k_eval7_smem<PHE_LAYOUT_MASKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr eval7 masks");
     chk(cudaFuncSetAttribute(k_enum7, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEnum), "attr enum7");
-    chk(cudaFuncSetAttribute(k_equity_mc_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr equity_mc");
+    chk(cudaFuncSetAttribute(k_equity_mc_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMc), "attr equity_mc");
     chk(cudaFuncSetAttribute(k_equity_plan_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr equity_plan");
     chk(cudaFuncSetAttribute(k_showdown_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr showdown");
 }
@@ -754,7 +775,7 @@ int phe_equity_mc(const uint64_t* states, int64_t n_states, int n_opp, uint64_t 
     } else {
         uint64_t ctas = (items + 31) / 32;
         if (ctas > (uint64_t)cx->sm_count) ctas = cx->sm_count;
-        k_equity_mc_smem<<<(unsigned)ctas, kCtaThreads, kSmemTabOnly, st>>>(cx->d_image, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk);
+        k_equity_mc_smem<<<(unsigned)ctas, kCtaThreads, kSmemMc, st>>>(cx->d_image, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk);
     }
     return after_launch("equity_mc launch");
 }
