@@ -79,6 +79,12 @@ int phe_eval7_host(const void *hands, int layout, int64_t n, uint16_t *ranks_out
  * may be NULL.  Shards of the index range may be summed in any order. */
 int phe_enum7(uint64_t *hist9, uint64_t *hist7463, uint64_t comb_begin, uint64_t comb_end, void *stream);
 int phe_enum7_host(uint64_t *hist9, uint64_t *hist7463, uint64_t comb_begin, uint64_t comb_end);
+/* Same range, but only part `part` of `nparts` interleaved parts: the range is cut into fixed tiles and tile t
+ * belongs to part t % nparts.  Low colex indices are the expensive ones (short blocks), so interleaved parts
+ * cost the same while contiguous halves do not; the parts' histograms add up to phe_enum7's exactly.  This is
+ * how the range is sharded over GPUs. */
+int phe_enum7_part(uint64_t *hist9, uint64_t *hist7463, uint64_t comb_begin, uint64_t comb_end,
+                   uint32_t part, uint32_t nparts, void *stream);
 
 /* ---- Monte-Carlo equity ------------------------------------------------- */
 /* For each state: deal the missing board cards and two cards to each of n_opp

@@ -319,3 +319,17 @@ def test_simulate_processes_service(phe, oracle, torch):
     assert results[("g2", "p0", 1)][3] == 97290 and results[("g2", "p1", 0)][3] == 98000
     r = results[("g2", "p1", 0)]
     assert abs(phe.winning_probability(r[4], r[3]) - 0.35) < 0.03          # 7-2 offsuit heads-up is about 35 %
+
+
+def test_enum7_interleaved_parts_add_up(phe, oracle, torch):
+    full9, full = phe.enumerate_c52_7(device_out=True)
+    for nparts in (2, 3, 8):
+        acc9, acc = torch.zeros_like(full9), torch.zeros_like(full)
+        for part in range(nparts):
+            a9, a = phe.enumerate_c52_7(device_out=True, part=part, nparts=nparts)
+            acc9 += a9; acc += a
+        assert bool((acc9 == full9).all()) and bool((acc == full).all())
+    a9, a = phe.enumerate_c52_7(1000, 5_000_000, device_out=True, part=1, nparts=2)
+    b9, b = phe.enumerate_c52_7(1000, 5_000_000, device_out=True, part=0, nparts=2)
+    o9, oh = oracle.enum7(1000, 5_000_000, nthreads=2)
+    assert ((a + b).cpu().numpy() == oh).all() and ((a9 + b9).cpu().numpy() == o9).all()

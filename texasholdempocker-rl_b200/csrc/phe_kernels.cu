@@ -180,11 +180,12 @@ __device__ __forceinline__ uint32_t enum_flush_addr(uint32_t x, uint32_t t, uint
 
 __global__ void __launch_bounds__(kCtaThreads, 1)
 k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_trimask, unsigned long long* __restrict__ hist9,
-        unsigned long long* __restrict__ hist7463, uint64_t begin, uint64_t end, uint32_t tile_size, unsigned int* __restrict__ tile_counter)
+        unsigned long long* __restrict__ hist7463, uint64_t begin, uint64_t end, uint32_t tile_size, uint32_t ntiles,
+        unsigned int* __restrict__ tile_counter, uint32_t part, uint32_t nparts)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + kEnumHistOff);
-    unsigned long long* s_h9 = reinterpret_cast<unsigned long long*>(smem + kEnumH9Off);
+    uint32_t* s_h9 = reinterpret_cast<uint32_t*>(smem + kEnumH9Off);   // per-CTA category counts fit 32 bits
     for (int i = threadIdx.x; i < kHistBinsPad; i += blockDim.x) s_hist[i] = 0;
     if (threadIdx.x < 9) s_h9[threadIdx.x] = 0;
     uint32_t* s_bin = reinterpret_cast<uint32_t*>(smem + kEnumBinOff);
@@ -203,16 +204,24 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
     // Dynamic tile scheduling: tiles of `tile_size` consecutive colex indices are handed out through an atomic
     // counter in increasing order.  Low indices hold the short blocks (small c3: few triples per block, poor lane
     // use), i.e. the expensive tiles go first and the cheap ones level the finish line.
-    const uint64_t total = end - begin;
-    const uint32_t ntiles = (uint32_t)((total + tile_size - 1) / tile_size);
     const uint32_t a_bin = sb + kEnumBinOff;
     for (;;) {
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(tile_counter, 1u);
-        tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+        tile = __shfl_sync(0xFFFFFFFFu, tile, 0) * nparts + part;   // this launch owns tiles == part (mod nparts)
         if (tile >= ntiles) break;
-        const uint64_t wb = begin + (uint64_t)tile * tile_size;
-        uint64_t we = wb + tile_size;
+        // graded tiles: tile t holds 64 + 4t hands until that reaches tile_size (the first, expensive hands are
+        // cut fine so that no single warp sits on a long serial tile), then tile_size hands each
+        const uint32_t t0 = (tile_size - 64u) >> 2;
+        uint64_t wb, we;
+        if (tile < t0) {
+            wb = begin + 64ull * tile + 2ull * tile * (tile - 1u + (tile == 0u));
+            we = wb + 64u + 4u * tile;
+        } else {
+            wb = begin + 64ull * t0 + 2ull * t0 * (t0 - 1u + (t0 == 0u)) + (uint64_t)(tile - t0) * tile_size;
+            we = wb + tile_size;
+        }
+        if (wb >= end) break;
         if (we > end) we = end;
         // warp-cooperative colex unrank: lane v (and v + 32) tests C(v, k) <= rem; the count of hits - 1 is c_i
         int c[7];
@@ -288,11 +297,11 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
         const uint32_t v = s_hist[i];
         if (v) {
             if (hist7463) atomicAdd(hist7463 + i, (unsigned long long)v);
-            if (hist9) atomicAdd(s_h9 + category_of(i), (unsigned long long)v);
+            if (hist9) atomicAdd(s_h9 + category_of(i), v);   // native 32-bit shared atomic (the 64-bit form is a CAS loop)
         }
     }
     __syncthreads();
-    if (hist9 && threadIdx.x < 9 && s_h9[threadIdx.x]) atomicAdd(hist9 + threadIdx.x, s_h9[threadIdx.x]);
+    if (hist9 && threadIdx.x < 9 && s_h9[threadIdx.x]) atomicAdd(hist9 + threadIdx.x, (unsigned long long)s_h9[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -706,26 +715,45 @@ int phe_eval7_host(const void* hands, int layout, int64_t n, uint16_t* out)
 }
 
 // ---- enum7 -------------------------------------------------------------------------------------
-int phe_enum7(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin, uint64_t comb_end, void* stream)
+int phe_enum7_part(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin, uint64_t comb_end, uint32_t part, uint32_t nparts,
+                   void* stream)
 {
-    if (comb_begin > comb_end || comb_end > PHE_NUM_HANDS_7) return PHE_EINVAL;
+    if (comb_begin > comb_end || comb_end > PHE_NUM_HANDS_7 || nparts == 0 || part >= nparts) return PHE_EINVAL;
     if (comb_begin == comb_end || (!hist9 && !hist7463)) return PHE_OK;
     DevCtx* cx = nullptr;
     int rc = current_ctx(&cx);
     if (rc) return rc;
     const uint64_t total = comb_end - comb_begin;
-    uint64_t ctas = (total + kCtaThreads * 64 - 1) / (kCtaThreads * 64);
+    // the tiling depends only on (range, nparts): about 8 tiles per resident warp of one part, but never fewer than
+    // 512 hands (per-tile unranking and partial blocks) nor more than 2048 (tail balance)
+    uint64_t tile = total / ((uint64_t)nparts * cx->sm_count * (kCtaThreads / 32) * 8);
+    if (tile < 512) tile = 512;
+    if (tile > 2048) tile = 2048;
+    tile &= ~(uint64_t)3;
+    // graded tiling (see k_enum7): sizes 64, 68, 72, ... up to `tile`, then constant
+    const uint64_t t0 = (tile - 64) / 4, s0 = 64 * t0 + (t0 ? 2 * t0 * (t0 - 1) : 0);
+    uint64_t ntiles;
+    if (total >= s0) ntiles = t0 + (total - s0 + tile - 1) / tile;
+    else {
+        ntiles = 0;
+        for (uint64_t covered = 0; covered < total; ntiles++) covered += 64 + 4 * ntiles;
+    }
+    const uint64_t mine = ntiles > part ? (ntiles - part + nparts - 1) / nparts : 0;
+    if (mine == 0) return PHE_OK;
+    uint64_t ctas = (mine + kCtaThreads / 32 - 1) / (kCtaThreads / 32);
     if (ctas > (uint64_t)cx->sm_count) ctas = cx->sm_count;
-    // ~24 tiles per resident warp, at least 256 hands each
-    uint64_t tile = total / (ctas * (kCtaThreads / 32) * 24);
-    if (tile < 256) tile = 256;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned int* counter = cx->d_counters + (cx->next_counter.fetch_add(1, std::memory_order_relaxed) % kCounterRing);
     PHE_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
     k_enum7<<<(unsigned)ctas, kCtaThreads, kSmemEnum, st>>>(
         cx->d_enum, cx->d_trimask, reinterpret_cast<unsigned long long*>(hist9), reinterpret_cast<unsigned long long*>(hist7463), comb_begin, comb_end,
-        (uint32_t)tile, counter);
+        (uint32_t)tile, (uint32_t)ntiles, counter, part, nparts);
     return after_launch("enum7 launch");
+}
+
+int phe_enum7(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin, uint64_t comb_end, void* stream)
+{
+    return phe_enum7_part(hist9, hist7463, comb_begin, comb_end, 0, 1, stream);
 }
 
 int phe_enum7_host(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin, uint64_t comb_end)

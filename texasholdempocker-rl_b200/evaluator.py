@@ -98,8 +98,11 @@ def eval7(hands, out=None):
     return res
 
 
-def enumerate_c52_7(comb_begin=0, comb_end=N.NUM_HANDS_7, device_out=False):
+def enumerate_c52_7(comb_begin=0, comb_end=N.NUM_HANDS_7, device_out=False, part=0, nparts=1):
     """Exhaustive evaluation of the 7-card combinations with colex index in [comb_begin, comb_end).
+
+    part / nparts select one of `nparts` interleaved, equally expensive parts of the range (device_out only); the
+    parts' histograms add up to the whole range's.
 
     Returns (hist9 int64[9], hist7463 int64[7463]): category counts (SF, quads, full house, flush, straight,
     trips, two pair, pair, high card) and the per-rank histogram (bin = rank, bin 0 empty).  With
@@ -109,8 +112,10 @@ def enumerate_c52_7(comb_begin=0, comb_end=N.NUM_HANDS_7, device_out=False):
     if device_out:
         buf = torch.zeros(9 + N.NUM_RANKS + 1, dtype=torch.int64, device="cuda")
         _use_device(buf.device.index)
-        N.check(L.phe_enum7(C.c_void_p(buf.data_ptr()), C.c_void_p(buf.data_ptr() + 72), comb_begin, comb_end, _stream_ptr()))
+        N.check(L.phe_enum7_part(C.c_void_p(buf.data_ptr()), C.c_void_p(buf.data_ptr() + 72), comb_begin, comb_end, int(part), int(nparts), _stream_ptr()))
         return buf[:9], buf[9:]
+    if nparts != 1:
+        raise ValueError("interleaved parts are a device_out feature")
     h9 = np.zeros(9, dtype=np.uint64)
     h = np.zeros(N.NUM_RANKS + 1, dtype=np.uint64)
     _use_device(_current_device())

@@ -44,13 +44,15 @@ def sharded_equity_mc(states, n_opp, rollouts, seed, sample_offset=0, group=None
 
 
 def sharded_enum7(group=None, local_fn=None, comb_begin=0, comb_end=N.NUM_HANDS_7, reduce=True):
-    """Rank r enumerates its contiguous slice of colex combination indices; histograms are all-reduced."""
+    """Rank r enumerates part r of `world` interleaved parts of the colex range (phe_enum7_part: equal cost per
+    rank, unlike contiguous slices, because the low indices hold the short, expensive blocks); histograms are
+    all-reduced.  local_fn(begin, end) (tests: the oracle) gets a contiguous slice instead."""
     from .evaluator import enumerate_c52_7
     rank, world = _world(group)
-    b, e = shard_range(comb_end - comb_begin, rank, world)
     if local_fn is None:
-        h9, h = enumerate_c52_7(comb_begin + b, comb_begin + e, device_out=True)
+        h9, h = enumerate_c52_7(comb_begin, comb_end, device_out=True, part=rank, nparts=world)
     else:
+        b, e = shard_range(comb_end - comb_begin, rank, world)
         h9, h = local_fn(comb_begin + b, comb_begin + e)
     if world > 1 and reduce:
         if not isinstance(h9, torch.Tensor):
