@@ -138,6 +138,21 @@ int phe_deal(const uint64_t *known, int64_t n, int need, uint64_t seed, uint64_t
 int phe_deal_host(const uint64_t *known, int64_t n, int need, uint64_t seed, uint64_t sample_offset,
                   uint32_t stream_base, uint8_t *cards_out);
 
+/* ---- terminal settlement (finish_game / _share_value, env/game.py:410-441, 560-632, 683-734) ---- */
+/* Per game: boards[g] (5-card set), holes[g][P] (2-card sets, every seat), actions[g][R][P] = last action of each
+ * betting round (0 None, 1 FOLD, 2 any other), values[g][R][P] = chips put in during the round, n_rounds[g] <= R,
+ * button[g] = seat index, onboard[g] = bit p set if seat p is still ONBOARD (odd-chip rule).  Outputs per seat: chips
+ * won, game result and pure card result in {-1 LOSE, 0 EVEN, 1 WIN}; paid_out[g] (optional) = seats present in the
+ * reference's winner_value_dict.  P <= 9, R <= 4. */
+int phe_settle(const uint64_t *boards, const uint64_t *holes, const int8_t *actions, const int32_t *values,
+               const int32_t *n_rounds, const int32_t *button, const uint32_t *onboard, int64_t n_games,
+               int n_players, int max_rounds, int small_blind, int32_t *won_out, int8_t *result_out,
+               int8_t *card_result_out, uint32_t *paid_out, void *stream);
+int phe_settle_host(const uint64_t *boards, const uint64_t *holes, const int8_t *actions, const int32_t *values,
+                    const int32_t *n_rounds, const int32_t *button, const uint32_t *onboard, int64_t n_games,
+                    int n_players, int max_rounds, int small_blind, int32_t *won_out, int8_t *result_out,
+                    int8_t *card_result_out, uint32_t *paid_out);
+
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
 uint64_t phe_launch_count(void);
 

@@ -22,7 +22,7 @@ SYMBOLS = [
     "phe_strerror", "phe_last_cuda_error", "phe_version", "phe_init",
     "phe_eval7", "phe_eval7_host", "phe_enum7", "phe_enum7_host", "phe_enum7_part",
     "phe_equity_mc", "phe_equity_mc_host", "phe_equity_plan", "phe_equity_plan_host", "phe_plan_num_deals",
-    "phe_showdown", "phe_showdown_host", "phe_deal", "phe_deal_host", "phe_launch_count",
+    "phe_showdown", "phe_showdown_host", "phe_deal", "phe_deal_host", "phe_settle", "phe_settle_host", "phe_launch_count",
 ]
 
 
@@ -61,6 +61,8 @@ def lib():
     L.phe_showdown_host.argtypes = [vp, vp, vp, i64, i32, vp, vp]; L.phe_showdown_host.restype = i32
     L.phe_deal.argtypes = [vp, i64, i32, u64, u64, u32, vp, vp]; L.phe_deal.restype = i32
     L.phe_deal_host.argtypes = [vp, i64, i32, u64, u64, u32, vp]; L.phe_deal_host.restype = i32
+    L.phe_settle.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp]; L.phe_settle.restype = i32
+    L.phe_settle_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, vp, vp, vp]; L.phe_settle_host.restype = i32
     L.phe_launch_count.restype = u64
     _lib = L
     return L

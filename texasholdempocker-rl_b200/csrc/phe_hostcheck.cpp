@@ -10,6 +10,7 @@
 #include "phe_core.cuh"
 #include "phe_enum.cuh"
 #include "phe_plan.h"
+#include "phe_settle.cuh"
 #include "phe_tables.h"
 
 using namespace phe;
@@ -125,6 +126,16 @@ void hc_enum7(uint64_t begin, uint64_t end, uint64_t* hist7463)
         t_start = 0;
         enum_block_next(c3, c4, c5, c6);
     }
+}
+
+// host instantiation of settle_game with ranks from the host-instantiated evaluator
+void hc_settle(uint64_t board, const uint64_t* holes, int P, int R, int button, int small_blind, uint32_t onboard, const int8_t* act,
+               const int32_t* val, int32_t* won, int8_t* result, int8_t* card, uint32_t* paid)
+{
+    GlobalTab tab{g_image.data()};
+    uint32_t ranks[SETTLE_MAX_PLAYERS];
+    for (int p = 0; p < P; p++) ranks[p] = eval7(board | holes[p], tab, g_hp);
+    settle_game(P, R, button, small_blind, onboard, ranks, act, val, won, result, card, paid);
 }
 
 uint64_t hc_plan_num_deals(int n_exist, const int32_t* plan, int n_steps)

@@ -17,6 +17,7 @@
 #include "phe_core.cuh"
 #include "phe_enum.cuh"
 #include "phe_plan.h"
+#include "phe_settle.cuh"
 #include "phe_tables.h"
 
 using namespace phe;
@@ -517,6 +518,42 @@ k_deal(const uint64_t* __restrict__ known, int64_t n, int need, uint64_t seed, u
 }
 
 // ------------------------------------------------------------------------------------------------
+// K6: terminal settlement (finish_game / _share_value).  One thread per game: P evaluations, then integer logic.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_settle(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict__ boards, const uint64_t* __restrict__ holes,
+         const int8_t* __restrict__ actions, const int32_t* __restrict__ values, const int32_t* __restrict__ n_rounds,
+         const int32_t* __restrict__ button, const uint32_t* __restrict__ onboard, int64_t n_games, int P, int R, int small_blind,
+         int32_t* __restrict__ won_out, int8_t* __restrict__ result_out, int8_t* __restrict__ card_out, uint32_t* __restrict__ paid_out)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_games) return;
+    const GlobalTab tab{g_tab};
+    const HashParams hp = c_hp;
+    const uint64_t board = boards[g];
+    uint32_t ranks[SETTLE_MAX_PLAYERS];
+    for (int p = 0; p < P; p++) ranks[p] = eval7(board | holes[g * P + p], tab, hp);
+    int8_t act[SETTLE_MAX_ROUNDS * SETTLE_MAX_PLAYERS];
+    int32_t val[SETTLE_MAX_ROUNDS * SETTLE_MAX_PLAYERS];
+    int nr = n_rounds[g];
+    nr = nr < 0 ? 0 : (nr > R ? R : nr);
+    for (int i = 0; i < nr * P; i++) {
+        act[i] = actions[g * R * P + i];
+        val[i] = values[g * R * P + i];
+    }
+    int32_t won[SETTLE_MAX_PLAYERS];
+    int8_t res[SETTLE_MAX_PLAYERS], card[SETTLE_MAX_PLAYERS];
+    uint32_t paid;
+    settle_game(P, nr, button[g], small_blind, onboard[g], ranks, act, val, won, res, card, &paid);
+    for (int p = 0; p < P; p++) {
+        won_out[g * P + p] = won[p];
+        result_out[g * P + p] = res[p];
+        card_out[g * P + p] = card[p];
+    }
+    if (paid_out) paid_out[g] = paid;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side: per-device context, error plumbing, launches
 // ------------------------------------------------------------------------------------------------
 namespace {
@@ -931,6 +968,66 @@ int phe_showdown_host(const uint64_t* boards, const uint64_t* holes, const uint3
         return rc;
     PHE_CUDA(cudaMemcpyAsync(winners_out, dout + o_win, G * 4, cudaMemcpyDeviceToHost, 0));
     if (ranks_out) PHE_CUDA(cudaMemcpyAsync(ranks_out, dout + o_ranks, G * P * 2, cudaMemcpyDeviceToHost, 0));
+    PHE_CUDA(cudaStreamSynchronize(0));
+    return PHE_OK;
+}
+
+// ---- settle ------------------------------------------------------------------------------------
+int phe_settle(const uint64_t* boards, const uint64_t* holes, const int8_t* actions, const int32_t* values, const int32_t* n_rounds,
+               const int32_t* button, const uint32_t* onboard, int64_t n_games, int n_players, int max_rounds, int small_blind,
+               int32_t* won_out, int8_t* result_out, int8_t* card_result_out, uint32_t* paid_out, void* stream)
+{
+    if (n_games < 0 || n_players < 1 || n_players > SETTLE_MAX_PLAYERS || max_rounds < 1 || max_rounds > SETTLE_MAX_ROUNDS || small_blind < 1)
+        return PHE_EINVAL;
+    if (n_games == 0) return PHE_OK;
+    if (!boards || !holes || !actions || !values || !n_rounds || !button || !onboard || !won_out || !result_out || !card_result_out)
+        return PHE_EINVAL;
+    DevCtx* cx = nullptr;
+    int rc = current_ctx(&cx);
+    if (rc) return rc;
+    const unsigned blocks = (unsigned)((n_games + 127) / 128);
+    k_settle<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(cx->d_image, boards, holes, actions, values, n_rounds, button, onboard, n_games,
+                                                                    n_players, max_rounds, small_blind, won_out, result_out, card_result_out, paid_out);
+    return after_launch("settle launch");
+}
+
+int phe_settle_host(const uint64_t* boards, const uint64_t* holes, const int8_t* actions, const int32_t* values, const int32_t* n_rounds,
+                    const int32_t* button, const uint32_t* onboard, int64_t n_games, int n_players, int max_rounds, int small_blind,
+                    int32_t* won_out, int8_t* result_out, int8_t* card_result_out, uint32_t* paid_out)
+{
+    if (n_games < 0 || n_players < 1 || n_players > SETTLE_MAX_PLAYERS || max_rounds < 1 || max_rounds > SETTLE_MAX_ROUNDS) return PHE_EINVAL;
+    if (n_games == 0) return PHE_OK;
+    if (!boards || !holes || !actions || !values || !n_rounds || !button || !onboard || !won_out || !result_out || !card_result_out)
+        return PHE_EINVAL;
+    const size_t G = (size_t)n_games, P = (size_t)n_players, R = (size_t)max_rounds;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += align256(bytes); return o; };
+    const size_t o_b = take(G * 8), o_h = take(G * P * 8), o_a = take(G * R * P), o_v = take(G * R * P * 4), o_n = take(G * 4), o_bt = take(G * 4),
+                 o_ob = take(G * 4);
+    const size_t in_bytes = off;
+    off = 0;
+    const size_t o_w = take(G * P * 4), o_r = take(G * P), o_c = take(G * P), o_p = take(G * 4);
+    const size_t out_bytes = off;
+    int rc;
+    if ((rc = t_in.ensure(in_bytes)) || (rc = t_out.ensure(out_bytes))) return rc;
+    char* di = static_cast<char*>(t_in.p);
+    char* dout = static_cast<char*>(t_out.p);
+    PHE_CUDA(cudaMemcpyAsync(di + o_b, boards, G * 8, cudaMemcpyHostToDevice, 0));
+    PHE_CUDA(cudaMemcpyAsync(di + o_h, holes, G * P * 8, cudaMemcpyHostToDevice, 0));
+    PHE_CUDA(cudaMemcpyAsync(di + o_a, actions, G * R * P, cudaMemcpyHostToDevice, 0));
+    PHE_CUDA(cudaMemcpyAsync(di + o_v, values, G * R * P * 4, cudaMemcpyHostToDevice, 0));
+    PHE_CUDA(cudaMemcpyAsync(di + o_n, n_rounds, G * 4, cudaMemcpyHostToDevice, 0));
+    PHE_CUDA(cudaMemcpyAsync(di + o_bt, button, G * 4, cudaMemcpyHostToDevice, 0));
+    PHE_CUDA(cudaMemcpyAsync(di + o_ob, onboard, G * 4, cudaMemcpyHostToDevice, 0));
+    if ((rc = phe_settle(reinterpret_cast<uint64_t*>(di + o_b), reinterpret_cast<uint64_t*>(di + o_h), reinterpret_cast<int8_t*>(di + o_a),
+                         reinterpret_cast<int32_t*>(di + o_v), reinterpret_cast<int32_t*>(di + o_n), reinterpret_cast<int32_t*>(di + o_bt),
+                         reinterpret_cast<uint32_t*>(di + o_ob), n_games, n_players, max_rounds, small_blind, reinterpret_cast<int32_t*>(dout + o_w),
+                         reinterpret_cast<int8_t*>(dout + o_r), reinterpret_cast<int8_t*>(dout + o_c), reinterpret_cast<uint32_t*>(dout + o_p), nullptr)))
+        return rc;
+    PHE_CUDA(cudaMemcpyAsync(won_out, dout + o_w, G * P * 4, cudaMemcpyDeviceToHost, 0));
+    PHE_CUDA(cudaMemcpyAsync(result_out, dout + o_r, G * P, cudaMemcpyDeviceToHost, 0));
+    PHE_CUDA(cudaMemcpyAsync(card_result_out, dout + o_c, G * P, cudaMemcpyDeviceToHost, 0));
+    if (paid_out) PHE_CUDA(cudaMemcpyAsync(paid_out, dout + o_p, G * 4, cudaMemcpyDeviceToHost, 0));
     PHE_CUDA(cudaStreamSynchronize(0));
     return PHE_OK;
 }
