@@ -55,6 +55,19 @@ def build_hostcheck(force=False):
     return HOSTCHECK
 
 
+PEAKS = os.path.join(LIBDIR, "phe_peaks")
+
+
+def build_peaks(force=False):
+    """On-box microbenchmarks for the integer / shared-memory roofline denominators (csrc/phe_peaks.cu)."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    src = os.path.join(CSRC, "phe_peaks.cu")
+    if force or _stale(PEAKS, [src]):
+        subprocess.check_call([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-o", PEAKS, src])
+    return PEAKS
+
+
 if __name__ == "__main__":
     print(build_library(force=True, verbose=True))
     print(build_hostcheck(force=True))
+    print(build_peaks(force=True))
