@@ -262,7 +262,13 @@ struct PlanDesc {
     int rnd_k;              // cards in the random step (0 = none)
     int rnd_n;              // draws per enumeration leaf
     uint64_t n_leaves;      // product of seg_count
+    // exhaustive plans whose last segment is the villain's two cards: the leaves of the segments before it
+    // ("prefix": board completions) are walked by warps, the C(.,2) villain hands by lanes over a pair table
+    int pair_tail;          // 1 if the fast path applies
+    uint64_t n_prefix;      // product of seg_count[0 .. n_seg-2]
 };
+
+constexpr uint32_t N_PAIRS = 1326;   // C(52,2): pair index q = C(c1,2) + c0, c0 < c1
 
 // exist: the task's known ids (deal order).  Fills cards[n_exist .. n_exist+n_enum) with the leaf's
 // enumerated ids in visiting order.  leaf numbering = reference visiting order.

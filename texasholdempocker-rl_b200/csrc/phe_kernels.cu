@@ -38,6 +38,7 @@ static constexpr uint32_t kEnumBarOff = kEnumH9Off + 9 * 8;                   //
 static constexpr uint32_t kEnumBinOff = kEnumBarOff + 16;                      // u32[8][64]: C(v, k) at [k*64 + v]
 static constexpr uint32_t kSmemEnum = kEnumBinOff + 8 * 64 * 4;
 static constexpr uint32_t kSmemTabOnly = kSmemTab + 16;
+static constexpr uint32_t kSmemPairs = kSmemTabOnly + N_PAIRS * 8;
 static constexpr uint32_t kSmemMc = kSmemTabOnly + MAX_DEAL * kCtaThreads;    // + one byte column per thread for dealt cards
 
 // ------------------------------------------------------------------------------------------------
@@ -456,6 +457,72 @@ k_equity_plan_gmem(const uint16_t* __restrict__ g_tab, const uint8_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// K3c: exhaustive plans ending in the villain's two cards (default rounds 2 and 3).  One warp per (task, board
+// completion): the prefix leaf is unranked once, the hero is ranked once, and the 32 lanes stride over the pair
+// table, skipping hands that touch a known card.  Visiting order differs from the reference's, counts do not.
+// ------------------------------------------------------------------------------------------------
+template <class Tab>
+__device__ __forceinline__ void equity_plan_pairs_body(const Tab& tab, const uint64_t* __restrict__ pairmask, const uint8_t* __restrict__ exist,
+                                                       int64_t n_tasks, const PlanDesc& pd, unsigned long long* __restrict__ wtl)
+{
+    const HashParams hp = c_hp;
+    const Binom C{c_binom};
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warps_per_cta = blockDim.x >> 5;
+    const uint64_t nwarps = (uint64_t)gridDim.x * warps_per_cta;
+    const uint64_t items = (uint64_t)n_tasks * pd.n_prefix;
+    PlanDesc prefix = pd;           // the plan without its last segment
+    prefix.n_seg = pd.n_seg - 1;
+    prefix.n_enum = pd.n_enum - 2;
+    for (uint64_t item = (uint64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); item < items; item += nwarps) {
+        const uint64_t task = item / pd.n_prefix, leaf = item - task * pd.n_prefix;
+        uint8_t cards[9];
+        for (int i = 0; i < pd.n_exist; i++) cards[i] = __ldg(exist + task * 8 + i);
+        plan_unrank_leaf(prefix, leaf, C, cards);
+        const uint64_t hero = id_bit(cards[0]) | id_bit(cards[1]);
+        const uint64_t board = id_bit(cards[2]) | id_bit(cards[3]) | id_bit(cards[4]) | id_bit(cards[5]) | id_bit(cards[6]);
+        const uint64_t known = hero | board;
+        const uint32_t hr = eval7(board | hero, tab, hp);
+        uint32_t w = 0, t = 0, l = 0;
+        for (uint32_t q = lane; q < N_PAIRS; q += 32) {
+            const uint64_t pm = pairmask[q];
+            if (pm & known) continue;
+            const uint32_t vr = eval7(board | pm, tab, hp);
+            w += hr < vr; t += hr == vr; l += hr > vr;
+        }
+        w = __reduce_add_sync(0xFFFFFFFFu, w);
+        t = __reduce_add_sync(0xFFFFFFFFu, t);
+        l = __reduce_add_sync(0xFFFFFFFFu, l);
+        if (lane == 0) {
+            if (w) atomicAdd(wtl + 3 * task + 0, (unsigned long long)w);
+            if (t) atomicAdd(wtl + 3 * task + 1, (unsigned long long)t);
+            if (l) atomicAdd(wtl + 3 * task + 2, (unsigned long long)l);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kCtaThreads, 1)
+k_equity_plan_pairs_smem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict__ g_pairmask, const uint8_t* __restrict__ exist,
+                         int64_t n_tasks, PlanDesc pd, unsigned long long* __restrict__ wtl)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* s_pairs = reinterpret_cast<uint64_t*>(smem + kSmemTabOnly);
+    for (uint32_t i = threadIdx.x; i < N_PAIRS; i += blockDim.x) s_pairs[i] = g_pairmask[i];
+    stage_tables(smem, g_tab, reinterpret_cast<uint64_t*>(smem + kSmemTab));   // includes a __syncthreads
+    __syncthreads();
+    const SharedTab tab{(uint32_t)__cvta_generic_to_shared(smem)};
+    equity_plan_pairs_body(tab, s_pairs, exist, n_tasks, pd, wtl);
+}
+
+__global__ void __launch_bounds__(256)
+k_equity_plan_pairs_gmem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict__ g_pairmask, const uint8_t* __restrict__ exist,
+                         int64_t n_tasks, PlanDesc pd, unsigned long long* __restrict__ wtl)
+{
+    const GlobalTab tab{g_tab};
+    equity_plan_pairs_body(tab, g_pairmask, exist, n_tasks, pd, wtl);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4: showdown (get_winner_set_v2, env/game.py:663-681).  One thread per game.
 // ------------------------------------------------------------------------------------------------
 template <class Tab>
@@ -567,6 +634,7 @@ struct DevCtx {
     uint16_t* d_image = nullptr;
     unsigned char* d_enum = nullptr;
     uint64_t* d_trimask = nullptr;
+    uint64_t* d_pairmask = nullptr;
     unsigned int* d_counters = nullptr;   // ring of tile counters, one per in-flight enumeration launch
     std::atomic<uint32_t> next_counter{0};
     int sm_count = 0;
@@ -629,6 +697,13 @@ void init_device(int device)
     chk(cudaMalloc(&cx.d_trimask, TRIMASK_BYTES), "cudaMalloc(trimask)");
     chk(cudaMemcpy(cx.d_trimask, g_trimask.data(), TRIMASK_BYTES, cudaMemcpyHostToDevice), "cudaMemcpy(trimask)");
     chk(cudaMalloc(&cx.d_counters, kCounterRing * sizeof(unsigned int)), "cudaMalloc(counters)");
+    {
+        std::vector<uint64_t> pm(N_PAIRS);
+        build_pairmask(pm.data());
+        chk(cudaMalloc(&cx.d_pairmask, N_PAIRS * 8), "cudaMalloc(pairmask)");
+        chk(cudaMemcpy(cx.d_pairmask, pm.data(), N_PAIRS * 8, cudaMemcpyHostToDevice), "cudaMemcpy(pairmask)");
+    }
+    chk(cudaFuncSetAttribute(k_equity_plan_pairs_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPairs), "attr equity_plan_pairs");
     chk(cudaMemcpyToSymbol(c_hp, &g_hp, sizeof g_hp), "cudaMemcpyToSymbol(c_hp)");
     chk(cudaMemcpyToSymbol(c_binom, g_binom, sizeof g_binom), "cudaMemcpyToSymbol(c_binom)");
     chk(cudaFuncSetAttribute(k_eval7_smem<PHE_LAYOUT_IDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr eval7 ids");
@@ -888,6 +963,19 @@ int phe_equity_plan(const uint8_t* exist, int n_exist, int64_t n_tasks, const in
     const double deals = (double)n_tasks * (double)plan_num_deals(pd);
     const uint64_t threads = (uint64_t)n_tasks * pd.n_leaves;
     auto* wp = reinterpret_cast<unsigned long long*>(wtl);
+    if (pd.pair_tail) {
+        const uint64_t items = (uint64_t)n_tasks * pd.n_prefix;   // one warp each
+        if (deals < 2.0e6) {
+            uint64_t blocks = (items + 7) / 8;
+            if (blocks > (uint64_t)cx->sm_count * 8) blocks = (uint64_t)cx->sm_count * 8;
+            k_equity_plan_pairs_gmem<<<(unsigned)blocks, 256, 0, st>>>(cx->d_image, cx->d_pairmask, exist, n_tasks, pd, wp);
+        } else {
+            uint64_t ctas = (items + 31) / 32;
+            if (ctas > (uint64_t)cx->sm_count) ctas = cx->sm_count;
+            k_equity_plan_pairs_smem<<<(unsigned)ctas, kCtaThreads, kSmemPairs, st>>>(cx->d_image, cx->d_pairmask, exist, n_tasks, pd, wp);
+        }
+        return after_launch("equity_plan (pair tail) launch");
+    }
     if (deals < 2.0e6) {
         uint64_t blocks = (threads + 255) / 256;
         if (blocks > (uint64_t)cx->sm_count * 8) blocks = (uint64_t)cx->sm_count * 8;

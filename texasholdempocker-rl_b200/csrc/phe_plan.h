@@ -61,6 +61,8 @@ inline bool parse_plan(int n_exist, const int32_t* plan, int n_steps, PlanDesc* 
         }
     }
     if (cards != 9) return false;
+    d.pair_tail = (d.rnd_k == 0 && d.n_seg >= 1 && d.seg_k[d.n_seg - 1] == 2) ? 1 : 0;
+    d.n_prefix = d.pair_tail ? d.n_leaves / d.seg_count[d.n_seg - 1] : 0;
     *pd = d;
     return true;
 }

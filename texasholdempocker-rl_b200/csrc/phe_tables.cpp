@@ -248,6 +248,12 @@ bool build_table_image(uint16_t* image, HashParams* hp_out)
     return false;
 }
 
+void build_pairmask(uint64_t out[N_PAIRS])
+{
+    for (int c1 = 1; c1 < 52; c1++)
+        for (int c0 = 0; c0 < c1; c0++) out[c1 * (c1 - 1) / 2 + c0] = id_bit(c0) | id_bit(c1);
+}
+
 // ---- enumeration image (phe_enum.cuh) --------------------------------------------------------
 static void fill_msrank(uint8_t cnt[13], int rank_from, int placed, uint32_t idx, uint16_t* ms)
 {
