@@ -288,6 +288,35 @@ def main():
                                                 "frac": n * 10 / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_eval": 10,
                                                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}}
             del masks, out
+            # --- the reference's equity tasks end to end (simulate_processes replacement, default plans) ---
+            from oracle import oracle as O
+            from oracle import pyport
+            rng = np.random.default_rng(0)
+            D = phe.DECK
+            tasks = []
+            for gid in range(128):          # a finished heads-up game emits 4 rounds x 2 players = 8 tasks (env/env.py:119-147)
+                cid = rng.permutation(52)[:9].tolist()
+                for p in range(2):
+                    hand = [D[i] for i in cid[2 * p: 2 * p + 2]]
+                    flop, turn, river = [D[i] for i in cid[4:7]], [D[cid[7]]], [D[cid[8]]]
+                    for rnd in range(4):
+                        tasks.append((gid, f"p{p}", rnd, flop if rnd >= 1 else None, turn if rnd >= 2 else None, river if rnd >= 3 else None, hand))
+            plans = {k: v for k, v in O.DEFAULT_PLANS.items()}
+            phe.solve_tasks(tasks[:16], plans)
+            t0 = time.perf_counter()
+            res = phe.solve_tasks(tasks, plans)
+            sdt = time.perf_counter() - t0
+            deals = sum(r[3] for r in res)
+            t0 = time.perf_counter()
+            pdeals = 0
+            for t in tasks[3:64:8]:          # eight river tasks through the pure-Python port, one core
+                ids_ = [phe.card_id(c) for c in t[6] + t[3] + t[4] + t[5]]
+                pdeals += pyport.run_plan(plans[3][0], ids_)[1]
+            pdt = time.perf_counter() - t0
+            extras["equity_service"] = {"value": len(tasks) / sdt, "unit": "tasks/s", "deals_per_s": deals / sdt, "tasks": len(tasks), "ms": sdt * 1e3,
+                                        "config": {"workload": "reference task tuples (env/env.py:240) -> result tuples (env/workflow.py:225), default plans, 128 games"},
+                                        "cpu_python_port": {"value": pdeals / pdt, "unit": "deals/s", "cores": 1,
+                                                            "sample": f"{pdeals} deals of river tasks through oracle/pyport.run_plan"}}
         barrier()
 
     if rank == 0:

@@ -62,8 +62,15 @@ def card_to_evaluator(card):
 
 
 def card_id(c):
-    """int id, 'As'-style text (phevaluator accepts both), or a Card-like object -> id in [0, 52)."""
-    if isinstance(c, (int, np.integer)):
+    """int id, 'As'-style text (phevaluator accepts both), or a Card-like object -> id in [0, 52).
+
+    Card objects (ours or the reference's env/cards.py Card) get their id memoised on the object: the Enum
+    ``.value`` descriptor look-ups of card_to_evaluator are the hot spot of the equity service's host side."""
+    if type(c) is int:
+        i = c
+    elif hasattr(c, "_phe_id"):
+        return c._phe_id
+    elif isinstance(c, (int, np.integer)):
         i = int(c)
     elif isinstance(c, str):
         if len(c) != 2 or c[0].upper() not in FIGURE_CHARS or c[1].upper() not in DECOR_CHARS:
@@ -71,6 +78,11 @@ def card_id(c):
         i = FIGURE_CHARS.index(c[0].upper()) * 4 + DECOR_CHARS.index(c[1].upper())
     else:
         i = card_to_evaluator(c)
+        if 0 <= i < NUM_CARDS:
+            try:
+                object.__setattr__(c, "_phe_id", i)
+            except Exception:  # noqa: BLE001  (objects with __slots__: just recompute next time)
+                pass
     if not 0 <= i < NUM_CARDS:
         raise ValueError(f"card id {i} out of range")
     return i

@@ -44,12 +44,12 @@ def solve_tasks(tasks, simulation_recurrent_param_dict, seed=0, stream_base=0):
         plan, num_estimation = simulation_recurrent_param_dict[rnd]
         exist = np.array([task_exist_ids(tasks[i]) for i in idxs], dtype=np.uint8)
         wtl = equity_plan(exist, plan, seed=seed, stream_base=stream_base + idxs[0])
+        # the reference asserts this too (env/workflow.py:223)
+        assert (wtl.sum(1) == num_estimation).all(), f"plan for round {rnd} does not generate {num_estimation} deals"
+        sums = (wtl[:, 0] - wtl[:, 2]).astype(np.float64).tolist()
         for row, i in enumerate(idxs):
-            n = int(wtl[row].sum())
-            # the reference asserts this too (env/workflow.py:223)
-            assert n == num_estimation, f"plan for round {rnd} generated {n} deals, config says {num_estimation}"
-            game_id, player_name = tasks[i][0], tasks[i][1]
-            results[i] = (game_id, player_name, rnd, num_estimation, float(int(wtl[row, 0]) - int(wtl[row, 2])))
+            t = tasks[i]
+            results[i] = (t[0], t[1], rnd, num_estimation, sums[row])
     return results
 
 
