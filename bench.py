@@ -114,7 +114,7 @@ def reference_arm(args):
     line = {
         "impl": "reference", "metric": "hand_evals_per_s", "value": val, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u16 ranks / u64 card sets", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": "exhaustive_c52_7 (bounded sample)", "hands_per_step": per_step},
         "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": "port",
                          "sample": f"{per_step} consecutive colex hands per step; pure-Python phevaluator algorithm + Python loop (oracle/pyport.py), "
@@ -161,7 +161,28 @@ def main():
     b, e = phe.shard_range(NUM_HANDS, rank, world)
     import ctypes as C
 
+    # N > 1: the all-reduce of the histograms is fused into the enumeration kernel (phe_enum7_allreduce: the last CTA
+    # exchanges the 60 KB through peer memory over NVLink).  If the symmetric-memory plumbing is unavailable the step
+    # falls back to kernel + NCCL all-reduce; `config.collective` says which one ran.
+    fused = None
+    if world > 1:
+        try:
+            fused = phe.FusedEnum7()
+            hist = fused.out
+        except Exception as ex:  # noqa: BLE001
+            fused = None
+            if rank == 0:
+                print(f"fused all-reduce unavailable ({type(ex).__name__}: {ex}); using NCCL", file=sys.stderr)
+        ok = torch.tensor([1 if fused is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            fused = None
+            hist = torch.zeros(9 + 7463, dtype=torch.int64, device=dev)
+
     def step():
+        if fused is not None:
+            fused.run()
+            return
         hist.zero_()
         phe._native.check(L.phe_enum7_part(C.c_void_p(hist.data_ptr()), C.c_void_p(hist.data_ptr() + 72), 0, NUM_HANDS, rank, world,
                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
@@ -225,7 +246,6 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
     value = NUM_HANDS * args.steps / (total_ms * 1e-3)
 
     extras = {}
@@ -319,6 +339,7 @@ def main():
                                                             "sample": f"{pdeals} deals of river tasks through oracle/pyport.run_plan"}}
         barrier()
 
+    clocks = sampler.stop() if rank == 0 else None   # sampled through the timed steps and the Monte-Carlo section
     if rank == 0:
         # --- e2e: the public host-buffer API (what a reference-side caller binds), results land in numpy ---
         t0 = time.perf_counter()
@@ -349,13 +370,15 @@ def main():
         line = {
             "metric": "hand_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u64 card sets -> u16 ranks (integer)", "data": "synthetic",
-            "config": {"workload": "exhaustive_c52_7", "hands_per_step": NUM_HANDS, "outputs": "int64[9] + int64[7463] histograms",
-                       "sharding": f"{world} interleaved tile sets of the colex combination range (phe_enum7_part)" + (" + all_reduce(int64[7472])" if world > 1 else ""),
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "exhaustive_c52_7", "hands_per_step": NUM_HANDS, "card_sets": "u64 bit sets -> u16 ranks", "outputs": "int64[9] + int64[7463] histograms",
+                       "sharding": f"{world} interleaved tile sets of the colex combination range (phe_enum7_part)",
+                       "collective": None if world == 1 else ("fused into k_enum7: peer-memory exchange of int64[7472] by the last CTA (phe_enum7_allreduce)"
+                                                              if fused is not None else "NCCL all_reduce(int64[7472])"),
                        "l2": "256 MB L2 flush between timed steps; hands are generated on chip (no HBM-resident input)",
-                       "launch": "step captured in a CUDA graph (memset + k_enum7" + (" + NCCL all-reduce)" if world > 1 else ")")},
+                       "launch": "step captured in a CUDA graph and replayed"},
             "roofline": {"bound": "int_issue", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T lane-ops/s",
-                         "frac": achieved / peak, "traffic": None, "algorithmic_lane_ops_per_eval": W_EVAL_LANE_OPS,
+                         "frac": achieved / peak, "traffic": hw["dram_bytes"] or None, "algorithmic_lane_ops_per_eval": W_EVAL_LANE_OPS,
                          "kernel_ms": kern_ms, "kernel": "k_enum7 (this rank's shard; median of 10 un-graphed launches)",
                          "peak_source": "profiles/int_peaks.json (measured LOP3+IMAD stream)" if "balanced_lane_ops_per_s" in int_peaks
                          else "nominal 148 SM x 128 lane-ops/clk x 1.965 GHz (no measured integer peak yet)",
@@ -376,7 +399,7 @@ def main():
         print(json.dumps(line))
     if world > 1:
         # drop the graph (it holds NCCL kernels) before the communicator goes away; never block the exit on teardown
-        del graph
+        del graph, fused
         torch.cuda.synchronize()
         dist.barrier()
         sys.stdout.flush()

@@ -86,6 +86,19 @@ int phe_enum7_host(uint64_t *hist9, uint64_t *hist7463, uint64_t comb_begin, uin
 int phe_enum7_part(uint64_t *hist9, uint64_t *hist7463, uint64_t comb_begin, uint64_t comb_end,
                    uint32_t part, uint32_t nparts, void *stream);
 
+/* Fused enumeration + all-reduce over peer memory (one kernel per GPU, no separate collective).  Rank `rank` of
+ * `world` (<= 8) enumerates its interleaved part of the range; the last CTA to finish pushes the rank's reduced
+ * 7472-bin histogram (9 category bins followed by the 7463 rank bins) into its slot of EVERY rank's workspace with
+ * peer stores over NVLink, raises a system-scope flag on each peer, waits for all peers' flags and sums the slots into
+ * out_hist7472 (device pointer, local).  peer_ws[r] is rank r's workspace (device pointer valid in this process:
+ * CUDA IPC / torch symmetric memory), each phe_enum7_allreduce_workspace() bytes, zeroed once before first use.
+ * The launch count (epoch) lives in the workspace, so the call may be captured in a CUDA graph and replayed; all
+ * ranks must issue the same sequence of calls.  A peer that does not show up within ~2 s makes bin 0 of the output
+ * UINT64_MAX instead of hanging. */
+uint64_t phe_enum7_allreduce_workspace(void);
+int phe_enum7_allreduce(uint64_t *out_hist7472, uint64_t comb_begin, uint64_t comb_end, int rank, int world,
+                        void *const *peer_ws, void *stream);
+
 /* ---- Monte-Carlo equity ------------------------------------------------- */
 /* For each state: deal the missing board cards and two cards to each of n_opp
  * opponents, `rollouts` times, global sample indices sample_offset ..

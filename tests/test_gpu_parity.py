@@ -333,3 +333,25 @@ def test_enum7_interleaved_parts_add_up(phe, oracle, torch):
     b9, b = phe.enumerate_c52_7(1000, 5_000_000, device_out=True, part=0, nparts=2)
     o9, oh = oracle.enum7(1000, 5_000_000, nthreads=2)
     assert ((a + b).cpu().numpy() == oh).all() and ((a9 + b9).cpu().numpy() == o9).all()
+
+
+def test_enum7_fused_allreduce_single_rank(phe, oracle, torch):
+    """phe_enum7_allreduce with world = 1: the last-CTA epilogue (slot exchange, flags, epoch) on one GPU; replayed
+    from a CUDA graph to check that the launch counter kept in device memory advances correctly."""
+    gold = json.load(open(os.path.join(GOLDEN, "hist7463.json")))
+    fe = phe.FusedEnum7()
+    for _ in range(3):
+        h9, h = fe.run()
+        torch.cuda.synchronize()
+        assert h9.tolist() == gold["hist9"] and h.tolist() == gold["hist7463"]
+    h9, h = fe.run(5, 250001)
+    torch.cuda.synchronize()
+    o9, oh = oracle.enum7(5, 250001, nthreads=2)
+    assert (h.cpu().numpy() == oh).all() and (h9.cpu().numpy() == o9).all()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fe.run()
+    for _ in range(4):
+        g.replay()
+    torch.cuda.synchronize()
+    assert fe.out[:9].tolist() == gold["hist9"] and fe.out[9:].tolist() == gold["hist7463"]

@@ -14,12 +14,12 @@ from .equity import deal, equity_mc, equity_plan, pack_states, plan_num_deals, r
 from .evaluator import enumerate_c52_7, eval7, evaluate_cards
 from .service import simulate_processes, solve_tasks, winning_probability
 from .settlement import settle, settle_env, settle_envs
-from .sharded import shard_range, sharded_enum7, sharded_equity_mc
+from .sharded import FusedEnum7, shard_range, sharded_enum7, sharded_equity_mc
 from .winner import GameEnv, GamePlayerResult, winner_sets
 
 __all__ = [
     "DECK", "Card", "CardDecor", "CardFigure", "card_id", "card_to_evaluator", "cards_to_mask", "ids_to_masks", "mask_to_ids",
     "deal", "equity_mc", "equity_plan", "pack_states", "plan_num_deals", "random_states", "showdown", "win_probability",
     "enumerate_c52_7", "eval7", "evaluate_cards", "simulate_processes", "solve_tasks", "winning_probability",
-    "settle", "settle_env", "settle_envs", "shard_range", "sharded_enum7", "sharded_equity_mc", "GameEnv", "GamePlayerResult", "winner_sets",
+    "settle", "settle_env", "settle_envs", "FusedEnum7", "shard_range", "sharded_enum7", "sharded_equity_mc", "GameEnv", "GamePlayerResult", "winner_sets",
 ]

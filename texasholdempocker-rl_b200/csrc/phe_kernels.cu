@@ -180,10 +180,82 @@ __device__ __forceinline__ uint32_t enum_flush_addr(uint32_t x, uint32_t t, uint
     return a_fl + 2u * suit_lane;
 }
 
+// ---- fused all-reduce epilogue (phe_enum7_allreduce) --------------------------------------------------------
+// Workspace of one rank (all ranks use the same layout; peers write into it through NVLink):
+//   slots  u64[2][8][7472]   histogram of source rank s for launches of parity p
+//   flags  u32[8]            flags[s] = number of the last launch whose slot from rank s is complete
+//   acc    u64[7472]         local accumulation target of the CTA flushes (zero between launches)
+//   epoch  u32, done u32     launch number (starts at 0 -> first launch is 1), CTA completion ticket
+constexpr int kAllBins = 9 + kHistBins;                       // 7472
+constexpr int kMaxWorld = 8;
+constexpr size_t kWsSlots = 0;
+constexpr size_t kWsFlags = kWsSlots + (size_t)2 * kMaxWorld * kAllBins * 8;
+constexpr size_t kWsAcc = kWsFlags + 64;
+constexpr size_t kWsEpoch = kWsAcc + (size_t)kAllBins * 8;
+constexpr size_t kWsBytes = kWsEpoch + 64;
+
+struct FusedArgs {
+    int rank, world;                       // world == 0: plain kernel, results go to hist9 / hist7463
+    unsigned char* ws[kMaxWorld];          // every rank's workspace
+    unsigned long long* out;               // local all-reduced histogram [7472]
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// executed by the last CTA of the launch, after every CTA's flush into acc is visible
+__device__ __forceinline__ void enum_allreduce_epilogue(const FusedArgs& fa)
+{
+    unsigned char* my = fa.ws[fa.rank];
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(my + kWsAcc);
+    uint32_t* epoch_p = reinterpret_cast<uint32_t*>(my + kWsEpoch);
+    uint32_t* done_p = epoch_p + 1;
+    const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_p) + 1u;
+    const size_t slot_off = kWsSlots + ((size_t)(e & 1u) * kMaxWorld + (size_t)fa.rank) * kAllBins * 8;
+    // 1. push this rank's histogram into its slot on every rank (peer stores), clear acc for the next launch
+    for (int i = threadIdx.x; i < kAllBins; i += blockDim.x) {
+        const unsigned long long v = __ldcg(acc + i);
+        acc[i] = 0;
+        for (int p = 0; p < fa.world; p++) reinterpret_cast<unsigned long long*>(fa.ws[p] + slot_off)[i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 2. tell every rank that slot (e, rank) is complete; 3. wait until all of this rank's slots of launch e are
+    if ((int)threadIdx.x < fa.world) {
+        st_release_sys(reinterpret_cast<uint32_t*>(fa.ws[threadIdx.x] + kWsFlags) + fa.rank, e);
+        const uint32_t* mine = reinterpret_cast<const uint32_t*>(my + kWsFlags) + threadIdx.x;
+        const long long t0 = clock64();
+        bool ok = true;
+        while ((int32_t)(ld_acquire_sys(mine) - e) < 0) {
+            if (clock64() - t0 > 4000000000ll) { ok = false; break; }   // ~2 s: a peer never launched
+            __nanosleep(200);
+        }
+        if (!ok) fa.out[0] = ~0ull;
+    }
+    __syncthreads();
+    __threadfence_system();
+    // 4. sum the slots
+    const unsigned char* base = my + kWsSlots + (size_t)(e & 1u) * kMaxWorld * kAllBins * 8;
+    for (int i = threadIdx.x; i < kAllBins; i += blockDim.x) {
+        unsigned long long sum = 0;
+        for (int s = 0; s < fa.world; s++) sum += __ldcg(reinterpret_cast<const unsigned long long*>(base + (size_t)s * kAllBins * 8) + i);
+        if (i != 0 || fa.out[0] != ~0ull) fa.out[i] = sum;
+    }
+    if (threadIdx.x == 0) {
+        *done_p = 0;
+        *epoch_p = e;
+    }
+}
+
 __global__ void __launch_bounds__(kCtaThreads, 1)
 k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_trimask, unsigned long long* __restrict__ hist9,
         unsigned long long* __restrict__ hist7463, uint64_t begin, uint64_t end, uint32_t tile_size, uint32_t ntiles,
-        unsigned int* __restrict__ tile_counter, uint32_t part, uint32_t nparts)
+        unsigned int* __restrict__ tile_counter, uint32_t part, uint32_t nparts, FusedArgs fa)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + kEnumHistOff);
@@ -304,6 +376,21 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
     }
     __syncthreads();
     if (hist9 && threadIdx.x < 9 && s_h9[threadIdx.x]) atomicAdd(hist9 + threadIdx.x, (unsigned long long)s_h9[threadIdx.x]);
+    if (fa.world > 0) {
+        // the CTA that takes the last completion ticket owns the all-reduce
+        __shared__ uint32_t s_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t* done_p = reinterpret_cast<uint32_t*>(fa.ws[fa.rank] + kWsEpoch) + 1;
+            s_last = atomicAdd(done_p, 1u) == gridDim.x - 1 ? 1u : 0u;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            enum_allreduce_epilogue(fa);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -827,11 +914,11 @@ int phe_eval7_host(const void* hands, int layout, int64_t n, uint16_t* out)
 }
 
 // ---- enum7 -------------------------------------------------------------------------------------
-int phe_enum7_part(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin, uint64_t comb_end, uint32_t part, uint32_t nparts,
-                   void* stream)
+static int launch_enum7(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin, uint64_t comb_end, uint32_t part, uint32_t nparts,
+                       const FusedArgs& fa, void* stream)
 {
     if (comb_begin > comb_end || comb_end > PHE_NUM_HANDS_7 || nparts == 0 || part >= nparts) return PHE_EINVAL;
-    if (comb_begin == comb_end || (!hist9 && !hist7463)) return PHE_OK;
+    if (fa.world == 0 && (comb_begin == comb_end || (!hist9 && !hist7463))) return PHE_OK;
     DevCtx* cx = nullptr;
     int rc = current_ctx(&cx);
     if (rc) return rc;
@@ -851,16 +938,42 @@ int phe_enum7_part(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin, uin
         for (uint64_t covered = 0; covered < total; ntiles++) covered += 64 + 4 * ntiles;
     }
     const uint64_t mine = ntiles > part ? (ntiles - part + nparts - 1) / nparts : 0;
-    if (mine == 0) return PHE_OK;
+    if (mine == 0 && fa.world == 0) return PHE_OK;
     uint64_t ctas = (mine + kCtaThreads / 32 - 1) / (kCtaThreads / 32);
+    if (ctas == 0) ctas = 1;   // fused mode: a rank without tiles still takes part in the all-reduce
     if (ctas > (uint64_t)cx->sm_count) ctas = cx->sm_count;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned int* counter = cx->d_counters + (cx->next_counter.fetch_add(1, std::memory_order_relaxed) % kCounterRing);
     PHE_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
     k_enum7<<<(unsigned)ctas, kCtaThreads, kSmemEnum, st>>>(
         cx->d_enum, cx->d_trimask, reinterpret_cast<unsigned long long*>(hist9), reinterpret_cast<unsigned long long*>(hist7463), comb_begin, comb_end,
-        (uint32_t)tile, (uint32_t)ntiles, counter, part, nparts);
+        (uint32_t)tile, (uint32_t)ntiles, counter, part, nparts, fa);
     return after_launch("enum7 launch");
+}
+
+int phe_enum7_part(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin, uint64_t comb_end, uint32_t part, uint32_t nparts,
+                   void* stream)
+{
+    FusedArgs fa{};
+    return launch_enum7(hist9, hist7463, comb_begin, comb_end, part, nparts, fa, stream);
+}
+
+uint64_t phe_enum7_allreduce_workspace(void) { return kWsBytes; }
+
+int phe_enum7_allreduce(uint64_t* out_hist7472, uint64_t comb_begin, uint64_t comb_end, int rank, int world, void* const* peer_ws,
+                        void* stream)
+{
+    if (!out_hist7472 || !peer_ws || world < 1 || world > kMaxWorld || rank < 0 || rank >= world) return PHE_EINVAL;
+    FusedArgs fa{};
+    fa.rank = rank;
+    fa.world = world;
+    for (int r = 0; r < world; r++) {
+        if (!peer_ws[r]) return PHE_EINVAL;
+        fa.ws[r] = static_cast<unsigned char*>(peer_ws[r]);
+    }
+    fa.out = reinterpret_cast<unsigned long long*>(out_hist7472);
+    auto* acc = reinterpret_cast<uint64_t*>(fa.ws[rank] + kWsAcc);
+    return launch_enum7(acc, acc + 9, comb_begin, comb_end, (uint32_t)rank, (uint32_t)world, fa, stream);
 }
 
 int phe_enum7(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin, uint64_t comb_end, void* stream)

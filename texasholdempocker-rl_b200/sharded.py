@@ -60,3 +60,39 @@ def sharded_enum7(group=None, local_fn=None, comb_begin=0, comb_end=N.NUM_HANDS_
         dist.all_reduce(h9, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
     return h9, h
+
+
+class FusedEnum7:
+    """Exhaustive enumeration sharded over the ranks of `group` with the histogram all-reduce fused into the
+    enumeration kernel (phe_enum7_allreduce): the last CTA of each rank's kernel exchanges the 60 KB histogram through
+    peer memory over NVLink, so a step is ONE kernel per GPU and can be captured in a CUDA graph.  torch's symmetric
+    memory provides the peer-mapped workspace (plumbing only); with one rank no peer mapping is needed."""
+
+    def __init__(self, group=None):
+        import ctypes as C
+        self.rank, self.world = _world(group)
+        L = N.lib()
+        nbytes = int(L.phe_enum7_allreduce_workspace())
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if self.world > 1:
+            import torch.distributed._symmetric_memory as symm
+            g = group if group is not None else dist.group.WORLD
+            self.ws = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+            self.handle = symm.rendezvous(self.ws, g.group_name if hasattr(g, "group_name") else g)
+            ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        else:
+            self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            ptrs = [self.ws.data_ptr()]
+        self.ws.zero_()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group)
+        self._ptrs = (C.c_void_p * self.world)(*ptrs)
+        self.out = torch.zeros(9 + N.NUM_RANKS + 1, dtype=torch.int64, device=dev)
+
+    def run(self, comb_begin=0, comb_end=N.NUM_HANDS_7):
+        """Launches on the current stream; returns views (hist9, hist7463) of the all-reduced result buffer."""
+        import ctypes as C
+        N.check(N.lib().phe_enum7_allreduce(C.c_void_p(self.out.data_ptr()), comb_begin, comb_end, self.rank, self.world, self._ptrs,
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return self.out[:9], self.out[9:]
