@@ -355,3 +355,36 @@ def test_enum7_fused_allreduce_single_rank(phe, oracle, torch):
         g.replay()
     torch.cuda.synchronize()
     assert fe.out[:9].tolist() == gold["hist9"] and fe.out[9:].tolist() == gold["hist7463"]
+
+
+def test_concurrent_callers(phe, oracle, torch):
+    """Many Python threads in one process (the reference runs its game loops as threads, env/workflow.py:848-878):
+    ctypes drops the GIL around every call, the library keeps per-thread scratch and no mutable global state."""
+    import threading
+    ids = rand_hands(50000, 9)
+    want = oracle.rank7_batch(ids)
+    masks = phe.ids_to_masks(ids)
+    st = phe.pack_states([["As", "Ah"]], [["2c", "7d", "Tc"]])
+    want_mc = oracle.equity_mc(int(st[0, 0]), int(st[0, 1]), 1, 3000, 5)
+    errors = []
+
+    def worker(k):
+        try:
+            for _ in range(5):
+                assert (phe.eval7(masks) == want).all()                                   # host entry point, per-thread scratch
+                assert phe.evaluate_cards(*ids[k].tolist()) == int(want[k])
+                assert (phe.equity_mc(st, 1, 3000, seed=5)[0] == want_mc).all()
+                s = torch.cuda.Stream()
+                with torch.cuda.stream(s):                                                   # device entry point on a private stream
+                    got = phe.eval7(torch.from_numpy(masks).cuda())
+                s.synchronize()
+                assert (got.cpu().numpy().astype(np.uint16) == want).all()
+        except Exception as ex:  # noqa: BLE001
+            errors.append(repr(ex))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
