@@ -185,7 +185,7 @@ __device__ __forceinline__ uint32_t enum_flush_addr(uint32_t x, uint32_t t, uint
 //   slots  u64[2][8][7472]   histogram of source rank s for launches of parity p
 //   flags  u32[8]            flags[s] = number of the last launch whose slot from rank s is complete
 //   acc    u64[7472]         local accumulation target of the CTA flushes (zero between launches)
-//   epoch  u32, done u32     launch number (starts at 0 -> first launch is 1), CTA completion ticket
+//   epoch  u32               launch number (starts at 0 -> first launch is 1)
 constexpr int kAllBins = 9 + kHistBins;                       // 7472
 constexpr int kMaxWorld = 8;
 constexpr size_t kWsSlots = 0;
@@ -214,7 +214,6 @@ __device__ __forceinline__ void enum_allreduce_epilogue(const FusedArgs& fa)
     unsigned char* my = fa.ws[fa.rank];
     unsigned long long* acc = reinterpret_cast<unsigned long long*>(my + kWsAcc);
     uint32_t* epoch_p = reinterpret_cast<uint32_t*>(my + kWsEpoch);
-    uint32_t* done_p = epoch_p + 1;
     const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_p) + 1u;
     const size_t slot_off = kWsSlots + ((size_t)(e & 1u) * kMaxWorld + (size_t)fa.rank) * kAllBins * 8;
     // 1. push this rank's histogram into its slot on every rank (peer stores), clear acc for the next launch
@@ -246,10 +245,7 @@ __device__ __forceinline__ void enum_allreduce_epilogue(const FusedArgs& fa)
         for (int s = 0; s < fa.world; s++) sum += __ldcg(reinterpret_cast<const unsigned long long*>(base + (size_t)s * kAllBins * 8) + i);
         if (i != 0 || fa.out[0] != ~0ull) fa.out[i] = sum;
     }
-    if (threadIdx.x == 0) {
-        *done_p = 0;
-        *epoch_p = e;
-    }
+    if (threadIdx.x == 0) *epoch_p = e;
 }
 
 __global__ void __launch_bounds__(kCtaThreads, 1)
@@ -376,17 +372,19 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
     }
     __syncthreads();
     if (hist9 && threadIdx.x < 9 && s_h9[threadIdx.x]) atomicAdd(hist9 + threadIdx.x, (unsigned long long)s_h9[threadIdx.x]);
-    if (fa.world > 0) {
-        // the CTA that takes the last completion ticket owns the all-reduce
-        __shared__ uint32_t s_last;
-        __threadfence();
-        __syncthreads();
+    // completion ticket: the last CTA re-arms the tile counter for the next launch (no memset node in front of the
+    // kernel) and, in fused mode, owns the all-reduce
+    __shared__ uint32_t s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(tile_counter + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
         if (threadIdx.x == 0) {
-            uint32_t* done_p = reinterpret_cast<uint32_t*>(fa.ws[fa.rank] + kWsEpoch) + 1;
-            s_last = atomicAdd(done_p, 1u) == gridDim.x - 1 ? 1u : 0u;
+            tile_counter[0] = 0;
+            tile_counter[1] = 0;
         }
-        __syncthreads();
-        if (s_last) {
+        if (fa.world > 0) {
             __threadfence();
             enum_allreduce_epilogue(fa);
         }
@@ -722,7 +720,7 @@ struct DevCtx {
     unsigned char* d_enum = nullptr;
     uint64_t* d_trimask = nullptr;
     uint64_t* d_pairmask = nullptr;
-    unsigned int* d_counters = nullptr;   // ring of tile counters, one per in-flight enumeration launch
+    unsigned int* d_counters = nullptr;   // ring of {tile counter, completion ticket} pairs, one per in-flight enumeration launch
     std::atomic<uint32_t> next_counter{0};
     int sm_count = 0;
 };
@@ -783,7 +781,8 @@ void init_device(int device)
     chk(cudaMemcpy(cx.d_enum, g_enum_image.data(), ENUM_IMG_BYTES, cudaMemcpyHostToDevice), "cudaMemcpy(enum tables)");
     chk(cudaMalloc(&cx.d_trimask, TRIMASK_BYTES), "cudaMalloc(trimask)");
     chk(cudaMemcpy(cx.d_trimask, g_trimask.data(), TRIMASK_BYTES, cudaMemcpyHostToDevice), "cudaMemcpy(trimask)");
-    chk(cudaMalloc(&cx.d_counters, kCounterRing * sizeof(unsigned int)), "cudaMalloc(counters)");
+    chk(cudaMalloc(&cx.d_counters, 2 * kCounterRing * sizeof(unsigned int)), "cudaMalloc(counters)");
+    chk(cudaMemset(cx.d_counters, 0, 2 * kCounterRing * sizeof(unsigned int)), "cudaMemset(counters)");
     {
         std::vector<uint64_t> pm(N_PAIRS);
         build_pairmask(pm.data());
@@ -943,8 +942,8 @@ static int launch_enum7(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin
     if (ctas == 0) ctas = 1;   // fused mode: a rank without tiles still takes part in the all-reduce
     if (ctas > (uint64_t)cx->sm_count) ctas = cx->sm_count;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    unsigned int* counter = cx->d_counters + (cx->next_counter.fetch_add(1, std::memory_order_relaxed) % kCounterRing);
-    PHE_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    // {tile counter, completion ticket}: zero at rest, re-armed by the kernel's last CTA
+    unsigned int* counter = cx->d_counters + 2 * (cx->next_counter.fetch_add(1, std::memory_order_relaxed) % kCounterRing);
     k_enum7<<<(unsigned)ctas, kCtaThreads, kSmemEnum, st>>>(
         cx->d_enum, cx->d_trimask, reinterpret_cast<unsigned long long*>(hist9), reinterpret_cast<unsigned long long*>(hist7463), comb_begin, comb_end,
         (uint32_t)tile, (uint32_t)ntiles, counter, part, nparts, fa);
