@@ -216,11 +216,24 @@ __device__ __forceinline__ void enum_allreduce_epilogue(const FusedArgs& fa)
     uint32_t* epoch_p = reinterpret_cast<uint32_t*>(my + kWsEpoch);
     const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_p) + 1u;
     const size_t slot_off = kWsSlots + ((size_t)(e & 1u) * kMaxWorld + (size_t)fa.rank) * kAllBins * 8;
-    // 1. push this rank's histogram into its slot on every rank (peer stores), clear acc for the next launch
-    for (int i = threadIdx.x; i < kAllBins; i += blockDim.x) {
-        const unsigned long long v = __ldcg(acc + i);
-        acc[i] = 0;
-        for (int p = 0; p < fa.world; p++) reinterpret_cast<unsigned long long*>(fa.ws[p] + slot_off)[i] = v;
+    // 1. push this rank's histogram into its slot on every rank (peer stores), clear acc for the next launch.
+    //    All loads are issued before the first store so that the L2 round trips overlap.
+    constexpr int kPer = (kAllBins + kCtaThreads - 1) / kCtaThreads;   // 8 bins per thread
+    {
+        unsigned long long v[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; k++) {
+            const int i = threadIdx.x + k * kCtaThreads;
+            v[k] = i < kAllBins ? __ldcg(acc + i) : 0ull;
+        }
+#pragma unroll
+        for (int k = 0; k < kPer; k++) {
+            const int i = threadIdx.x + k * kCtaThreads;
+            if (i < kAllBins) {
+                acc[i] = 0;
+                for (int p = 0; p < fa.world; p++) reinterpret_cast<unsigned long long*>(fa.ws[p] + slot_off)[i] = v[k];
+            }
+        }
     }
     __threadfence_system();
     __syncthreads();
@@ -238,12 +251,24 @@ __device__ __forceinline__ void enum_allreduce_epilogue(const FusedArgs& fa)
     }
     __syncthreads();
     __threadfence_system();
-    // 4. sum the slots
+    // 4. sum the slots (again: all loads of a bin group in flight together)
     const unsigned char* base = my + kWsSlots + (size_t)(e & 1u) * kMaxWorld * kAllBins * 8;
-    for (int i = threadIdx.x; i < kAllBins; i += blockDim.x) {
-        unsigned long long sum = 0;
-        for (int s = 0; s < fa.world; s++) sum += __ldcg(reinterpret_cast<const unsigned long long*>(base + (size_t)s * kAllBins * 8) + i);
-        if (i != 0 || fa.out[0] != ~0ull) fa.out[i] = sum;
+    const bool failed = fa.out[0] == ~0ull;
+    unsigned long long sum[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; k++) sum[k] = 0;
+    for (int s = 0; s < fa.world; s++) {
+        const unsigned long long* slot = reinterpret_cast<const unsigned long long*>(base + (size_t)s * kAllBins * 8);
+#pragma unroll
+        for (int k = 0; k < kPer; k++) {
+            const int i = threadIdx.x + k * kCtaThreads;
+            if (i < kAllBins) sum[k] += __ldcg(slot + i);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; k++) {
+        const int i = threadIdx.x + k * kCtaThreads;
+        if (i < kAllBins && !(failed && i == 0)) fa.out[i] = sum[k];
     }
     if (threadIdx.x == 0) *epoch_p = e;
 }
