@@ -56,7 +56,7 @@ extern "C" {
 #define PHE_NUM_RANKS     7462
 #define PHE_NUM_HANDS_7   133784560ull   /* C(52,7) */
 #define PHE_MAX_PLAYERS   9    /* hero + 8 opponents: 5 + 2*8 = 21 dealt cards at most */
-#define PHE_MAX_PLAN_STEPS 8
+#define PHE_MAX_PLAN_STEPS 8   /* rows of an equity plan */
 
 const char *phe_strerror(int status);
 const char *phe_last_cuda_error(void);       /* thread-local text of the last PHE_ECUDA */

@@ -39,7 +39,6 @@ constexpr uint32_t TAB_BYTES = TAB_U16 * 2;
 // multipliers of the two hash functions (found by the table builder, verified collision free)
 struct HashParams { uint32_t a1, b1, a2, b2; };
 
-constexpr uint64_t NONCARD_BITS = 0xE000E000E000E000ull;   // rank nibble values 13..15
 constexpr uint64_t CARD_BITS = 0x1FFF1FFF1FFF1FFFull;
 
 PHE_HD int popc32(uint32_t x)

@@ -1,10 +1,11 @@
 // phe_kernels.cu -- sm_100a kernels and the C ABI declared in include/phe_b200.h.
 //
 // All kernels are integer / shared-memory-lookup work (no tensor cores): card sets are 64-bit
-// words, the 160 KB rank-table image is staged into shared memory once per CTA with a TMA bulk
-// copy (cp.async.bulk + mbarrier), grids are persistent (one 1024-thread CTA per SM), counts are
-// reduced with redux/shuffles before any atomic.  There is no host compute path: every entry
-// point either launches a kernel or returns an error.
+// words, the rank-table images (160 KB generic, 190 KB enumeration) are staged into shared memory
+// once per CTA with a TMA bulk copy (cp.async.bulk + mbarrier), grids are persistent (one
+// 1024-thread CTA per SM), counts are reduced with redux/shuffles before any atomic, and the
+// enumeration's histogram all-reduce is fused into its kernel over peer memory.  There is no host
+// compute path: every entry point either launches a kernel or returns an error.
 #include <cuda_runtime.h>
 
 #include <atomic>
