@@ -417,3 +417,12 @@ def test_eval7_and_enum7_agree_on_a_colex_slice(phe, oracle, torch):
     h9, h = phe.enumerate_c52_7(b, b + n)
     assert (np.bincount(ranks, minlength=7463) == h).all()
     assert int(h9.sum()) == n
+
+
+def test_deal_on_garbage_input_terminates(phe, torch):
+    """A `known` set that leaves fewer free cards than requested cannot be dealt; the kernel must give up, not spin."""
+    full = int(0x1FFF1FFF1FFF1FFF)
+    known = torch.tensor([full & ~0b111, full], dtype=torch.int64).cuda()        # 3 free cards / no free card
+    out = phe.deal(known, 9, seed=1)
+    torch.cuda.synchronize()
+    assert out.shape == (2, 9)

@@ -85,3 +85,13 @@ def test_shard_range_tiles(phe):
             edges = [phe.shard_range(total, r, world) for r in range(world)]
             assert edges[0][0] == 0 and edges[-1][1] == total
             assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+
+
+def test_equity_mc_rejects_malformed_numpy_states(phe):
+    good = phe.pack_states([["As", "Ah"]], [["2c", "7d", "Tc"]])
+    for bad in (np.array([[good[0, 0], 0]]), np.array([[good[0, 0] | (1 << 13), good[0, 1]]]),
+                np.array([[good[0, 1], good[0, 0]]]), np.array([[good[0, 0] | 0xF, good[0, 1]]])):
+        with pytest.raises(ValueError):
+            phe.equity_mc(bad.astype(np.int64), 1, 10, seed=1)
+    with pytest.raises(ValueError):
+        phe.equity_mc(good, 9, 10, seed=1)

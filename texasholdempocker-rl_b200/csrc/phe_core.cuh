@@ -148,7 +148,8 @@ PHE_UNROLL
 // draws: suit_j = (w >> 2j) & 3 from the low ten bits, and v = w >> 10 gives rank_j as the base-13 digits of v,
 // least significant first.  A word with v >= 11 * 13^5 is skipped whole (2.6 %), which makes the digits exactly
 // uniform.  Draw j addresses card-set bit 16*suit_j + rank_j and is accepted iff that bit is clear in the running
-// used set; accepted positions are stored in order.  Words are consumed until `need` cards are accepted.
+// used set; accepted positions are stored in order.  Words are consumed until `need` cards are accepted (or 64
+// blocks have been used, which only malformed input can reach).
 constexpr int MAX_DEAL = 21;
 constexpr uint32_t DEAL_V_LIMIT = 11u * 371293u;   // 11 * 13^5 = 4,084,223 <= 2^22
 
@@ -163,7 +164,8 @@ PHE_HD void deal_cards(uint64_t known, uint64_t seed, uint64_t sample, uint32_t 
 {
     uint32_t used_lo = (uint32_t)known, used_hi = (uint32_t)(known >> 32);
     int got = 0;
-    for (uint32_t blk = 0; got < need; blk++) {
+    // 64 blocks = 1280 draws: never reached with a valid state (>= 31 of 52 cards free); bounds the loop on garbage
+    for (uint32_t blk = 0; got < need && blk < 64u; blk++) {
         uint32_t rnd[4];
         philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), stream, blk, (uint32_t)seed, (uint32_t)(seed >> 32), rnd);
 PHE_UNROLL

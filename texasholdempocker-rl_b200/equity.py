@@ -62,6 +62,24 @@ def random_states(n_states, seed, streets=(0, 3, 4, 5)):
     return np.stack([hero | board, hero], axis=1).astype(np.int64)
 
 
+_CARD_BITS = np.uint64(0x1FFF1FFF1FFF1FFF)
+
+
+def _validate_states(a, n_opp):
+    """Host-side check of numpy states (device tensors are the caller's responsibility)."""
+    u = a.view(np.uint64)
+    known, hero = u[:, 0], u[:, 1] & _CARD_BITS
+    over = (u[:, 1] >> np.uint64(61)).astype(np.int64)
+    nk = np.bitwise_count(known)
+    if ((known & ~_CARD_BITS) != 0).any() or not np.isin(nk, (2, 5, 6, 7)).all():
+        raise ValueError("known must hold the hero's two cards plus 0, 3, 4 or 5 board cards")
+    if (np.bitwise_count(hero) != 2).any() or ((hero & known) != hero).any():
+        raise ValueError("hero must be two cards contained in known")
+    k = np.where(over > 0, over, n_opp)
+    if (k < 1).any() or (k > 8).any():
+        raise ValueError("opponent count must be 1..8")
+
+
 def equity_mc(states, n_opp, rollouts, seed, sample_offset=0, state_index_base=0, out=None):
     """states int64[S,2] (see pack_states) -> counts int64[S,3] = (win, tie, loss) over `rollouts` deals.
 
@@ -84,6 +102,7 @@ def equity_mc(states, n_opp, rollouts, seed, sample_offset=0, state_index_base=0
     a = np.ascontiguousarray(np.asarray(states, dtype=np.int64))
     if a.ndim != 2 or a.shape[1] != 2:
         raise ValueError("states must be int64[S,2]")
+    _validate_states(a, int(n_opp))
     res = np.zeros((a.shape[0], 3), dtype=np.uint64)
     _use_device(_current_device())
     N.check(L.phe_equity_mc_host(_np_ptr(a), a.shape[0], int(n_opp), int(rollouts), int(sample_offset),
