@@ -419,16 +419,17 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* The dealing stream the CUDA kernels use (DESIGN.md "RNG stream"):
- *   Philox block b = philox4x32_10(counter = (sample lo32, sample hi32, stream id, b), key = (seed lo32, seed hi32)).
- *   Every 32-bit output word w (words 0..3 of block 0, then block 1, ...) carries five draws:
- *     suit_j = (w >> 2j) & 3 (low ten bits), rank_j = j-th base-13 digit of v = w >> 10, least significant first;
- *     a word with v >= 11 * 13^5 is skipped whole, so that the five digits are exactly uniform.
- *   Draw j addresses bit 16*suit_j + rank_j of the 64-bit card-set word and is accepted iff that bit is clear in
- *   `used` (initially the known cards); accepted cards fill, in order, the missing board cards and then two
- *   hole cards per opponent.  Words are consumed until enough cards are accepted. */
-#define DEAL_V_LIMIT (11u * 371293u)
-
+/* The dealing stream the CUDA kernels use (DESIGN.md "RNG stream"), restated.
+ *   A deal is a sequence of slots: at most one single card, then pairs.  Philox block b = philox4x32_10(counter =
+ *   (sample lo32, sample hi32, stream id, b), key = (seed lo32, seed hi32)); its four words give eight 16-bit draws,
+ *   low half first.
+ *   single slot (if asked for): draws 0 and 1 of block 0 are reserved for it; draw r is valid if r < 1260*52 and
+ *     proposes card id r % 52; the first valid proposal whose card is free is taken; if neither works, further
+ *     draws come from blocks 0x80000000, 0x80000001, ...
+ *   pair slots, in order: draws continue after the reserved word (from draw 0 if there is no single); r is valid if
+ *     r < 49*1326 and proposes the pair with index r % 1326 (index C(c1,2)+c0 over ids c0 < c1), accepted iff both
+ *     cards are free.  Accepted slots mark their cards used.
+ *   Hold'em roles: single + first pairs = missing board cards, remaining pairs = opponents in order. */
 static inline uint8_t bit_to_id(int b) { return (uint8_t)((b & 15) * 4 + (b >> 4)); }
 static inline int id_to_bit(int id) { return 16 * (id & 3) + (id >> 2); }
 
@@ -439,37 +440,61 @@ static int mask_to_ids(uint64_t m, uint8_t *out, int cap)
     return k;
 }
 
-/* deal `need` cards with the shared stream; returns them as bit positions */
-static void deal_shared(uint64_t known, uint64_t seed, uint64_t sample, uint32_t stream, int need, int *bits)
+static void pair_from_index(uint32_t q, int *c0, int *c1)
+{
+    int hi = 1;
+    while ((uint32_t)((hi + 1) * hi / 2) <= q) hi++;
+    *c1 = hi; *c0 = (int)q - hi * (hi - 1) / 2;
+}
+
+/* deals `want_single` + n_pairs slots; ids_out = [single?][pair0 lo, pair0 hi][pair1 ...] (pairs as sorted ids) */
+static void deal_shared(uint64_t known, uint64_t seed, uint64_t sample, uint32_t stream, int want_single, int n_pairs, uint8_t *ids_out)
 {
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t ctr[4] = {(uint32_t)sample, (uint32_t)(sample >> 32), stream, 0};
+    uint32_t out[4];
     uint64_t used = known;
-    int got = 0;
-    while (got < need) {
-        uint32_t out[4];
-        orc_philox4x32_10(ctr, key, out);
-        ctr[3]++;
-        for (int wi = 0; wi < 4 && got < need; wi++) {
-            uint32_t w = out[wi], v = w >> 10;
-            if (v >= DEAL_V_LIMIT) continue;
-            for (int j = 0; j < 5 && got < need; j++) {
-                int rank = (int)(v % 13u), suit = (int)((w >> (2 * j)) & 3u);
-                v /= 13u;
-                int pos = 16 * suit + rank;
-                if (used >> pos & 1) continue;
-                used |= 1ull << pos;
-                bits[got++] = pos;
+    int n = 0;
+    orc_philox4x32_10(ctr, key, out);
+    if (want_single) {
+        int have = 0;
+        for (int h = 0; h < 2 && !have; h++) {
+            uint32_t r = (out[0] >> (16 * h)) & 0xFFFFu;
+            int c = (int)(r % 52u);
+            if (r < 1260u * 52u && !(used >> id_to_bit(c) & 1)) { have = 1; used |= 1ull << id_to_bit(c); ids_out[n++] = (uint8_t)c; }
+        }
+        for (uint32_t t = 0; !have; t++) {
+            uint32_t c2[4] = {ctr[0], ctr[1], ctr[2], 0x80000000u + t}, ex[4];
+            orc_philox4x32_10(c2, key, ex);
+            for (int d = 0; d < 8 && !have; d++) {
+                uint32_t r = (ex[d >> 1] >> (16 * (d & 1))) & 0xFFFFu;
+                int c = (int)(r % 52u);
+                if (r < 1260u * 52u && !(used >> id_to_bit(c) & 1)) { have = 1; used |= 1ull << id_to_bit(c); ids_out[n++] = (uint8_t)c; }
             }
         }
+    }
+    int got = 0, first_word = want_single ? 1 : 0;
+    for (uint32_t blk = 0; got < n_pairs; blk++) {
+        if (blk) { ctr[3] = blk; orc_philox4x32_10(ctr, key, out); }
+        for (int wi = first_word; wi < 4 && got < n_pairs; wi++)
+            for (int h = 0; h < 2 && got < n_pairs; h++) {
+                uint32_t r = (out[wi] >> (16 * h)) & 0xFFFFu;
+                if (r >= 49u * 1326u) continue;
+                int c0, c1;
+                pair_from_index(r % 1326u, &c0, &c1);
+                uint64_t m = (1ull << id_to_bit(c0)) | (1ull << id_to_bit(c1));
+                if (m & used) continue;
+                used |= m;
+                ids_out[n++] = (uint8_t)c0; ids_out[n++] = (uint8_t)c1;
+                got++;
+            }
+        first_word = 0;
     }
 }
 
 void orc_deal(uint64_t known, uint64_t seed, uint64_t sample, uint32_t stream, int need, uint8_t *ids_out)
 {
-    int bits[64];
-    deal_shared(known, seed, sample, stream, need, bits);
-    for (int i = 0; i < need; i++) ids_out[i] = bit_to_id(bits[i]);
+    deal_shared(known, seed, sample, stream, need & 1, need >> 1, ids_out);
 }
 
 /* Monte-Carlo equity of one state with the shared stream; bit-exact partner of
@@ -483,20 +508,20 @@ void orc_equity_mc(uint64_t known, uint64_t hero, int n_opp, uint64_t rollouts, 
     uint8_t hero_ids[2], board_ids[5];
     mask_to_ids(hero, hero_ids, 2);
     int nb = mask_to_ids(known & ~hero, board_ids, 5);
-    int need = (5 - nb) + 2 * n_opp;
+    int nbm = 5 - nb;
     wtl[0] = wtl[1] = wtl[2] = 0;
     for (uint64_t s = 0; s < rollouts; s++) {
-        int bits[64];
-        deal_shared(known, seed, sample_offset + s, state_idx, need, bits);
+        uint8_t dealt[32];
+        deal_shared(known, seed, sample_offset + s, state_idx, nbm & 1, nbm / 2 + n_opp, dealt);
         uint8_t c[7];
         int k = 0;
         for (int i = 0; i < nb; i++) c[i] = board_ids[i];
-        for (int i = nb; i < 5; i++) c[i] = bit_to_id(bits[k++]);
+        for (int i = nb; i < 5; i++) c[i] = dealt[k++];      /* single + board pairs complete the board */
         c[5] = hero_ids[0]; c[6] = hero_ids[1];
         int hr = orc_rank7(c);
         int best = 1 << 30;
         for (int o = 0; o < n_opp; o++) {
-            c[5] = bit_to_id(bits[k++]); c[6] = bit_to_id(bits[k++]);
+            c[5] = dealt[k++]; c[6] = dealt[k++];
             int r = orc_rank7(c);
             if (r < best) best = r;
         }
@@ -601,9 +626,8 @@ static void plan_rec(plan_ctx *cx, int step, uint8_t *cards, int ncards, int sta
         uint64_t known_bits = 0;
         for (int i = 0; i < ncards; i++) known_bits |= 1ull << id_to_bit(cards[i]);
         for (int j = 0; j < nrand; j++) {
-            int bits[16];
-            deal_shared(known_bits, cx->seed, cx->rnd_leaf * (uint64_t)nrand + (uint64_t)j, cx->stream, gen, bits);
-            for (int i = 0; i < gen; i++) cards[ncards + i] = bit_to_id(bits[i]);
+            /* [single?][pairs...]: the last pair is the villain's hand, everything before it completes the board */
+            deal_shared(known_bits, cx->seed, cx->rnd_leaf * (uint64_t)nrand + (uint64_t)j, cx->stream, gen & 1, gen >> 1, cards + ncards);
             plan_leaf(cx, cards);
         }
         cx->rnd_leaf++;

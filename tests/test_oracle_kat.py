@@ -98,19 +98,38 @@ def test_k8_aces_preflop(oracle):
         assert abs(p - 0.852) < 3 * (0.25 / 400000) ** 0.5 + 0.001
 
 
-def test_shared_stream_is_uniform(oracle):
-    # every unknown card is dealt equally often (chi-square, 3-sigma-ish bound)
-    known = oracle.mask_of(oracle.ids("As Ah 2c 7d Tc"))
+@pytest.mark.parametrize("need", [1, 4, 5])
+def test_shared_stream_is_uniform(oracle, need):
+    # every unknown card is dealt equally often, for even counts (pairs only) and odd ones (single + pairs)
+    known_ids = oracle.ids("As Ah 2c 7d Tc")
+    known = oracle.mask_of(known_ids)
     counts = np.zeros(52)
     n = 40000
     for s in range(n):
-        for c in oracle.deal(known, 99, s, 0, 4):
+        row = oracle.deal(known, 99, s, 0, need)
+        assert len(set(row.tolist())) == need
+        for c in row:
             counts[c] += 1
-    assert counts[oracle.ids("As Ah 2c 7d Tc")].sum() == 0
-    free = np.delete(counts, oracle.ids("As Ah 2c 7d Tc"))
-    exp = n * 4 / 47
+    assert counts[known_ids].sum() == 0
+    free = np.delete(counts, known_ids)
+    exp = n * need / 47
     chi2 = ((free - exp) ** 2 / exp).sum()
     assert chi2 < 46 + 4 * (2 * 46) ** 0.5
+
+
+def test_shared_stream_pairs_are_uniform(oracle):
+    # the two cards of a pair slot are a uniform unordered pair of the free cards
+    known = oracle.mask_of(oracle.ids("As Ah 2c 7d Tc 3h 9s"))
+    seen = {}
+    n = 60000
+    for s in range(n):
+        a, b = oracle.deal(known, 5, s, 1, 2).tolist()
+        assert a < b
+        seen[(a, b)] = seen.get((a, b), 0) + 1
+    assert len(seen) == 990
+    exp = n / 990
+    chi2 = sum((v - exp) ** 2 / exp for v in seen.values())
+    assert chi2 < 989 + 4 * (2 * 989) ** 0.5
 
 
 def test_winner_mask_semantics(oracle):

@@ -142,76 +142,146 @@ PHE_UNROLL
 }
 
 // ---- dealing -----------------------------------------------------------------------------------
-// Draws `need` (<= 21) distinct cards outside `known` for (seed, stream, sample); exactly uniform over the
-// unknown cards, a pure function of its arguments.  Philox block b = philox(counter (sample lo, sample hi,
-// stream, b), key seed).  Every 32-bit output word w (words 0..3 of block 0, then block 1, ...) carries five
-// draws: suit_j = (w >> 2j) & 3 from the low ten bits, and v = w >> 10 gives rank_j as the base-13 digits of v,
-// least significant first.  A word with v >= 11 * 13^5 is skipped whole (2.6 %), which makes the digits exactly
-// uniform.  Draw j addresses card-set bit 16*suit_j + rank_j and is accepted iff that bit is clear in the running
-// used set; accepted positions are stored in order.  Words are consumed until `need` cards are accepted (or 64
-// blocks have been used, which only malformed input can reach).
-constexpr int MAX_DEAL = 21;
-constexpr uint32_t DEAL_V_LIMIT = 11u * 371293u;   // 11 * 13^5 = 4,084,223 <= 2^22
+// A deal is a sequence of SLOTS: at most one single card, then pairs.  Drawing an unordered pair uniformly among the
+// free pairs, one pair after another, is the same distribution as dealing the cards one by one -- and a hold'em deal
+// only ever needs unordered groups: the missing board cards (as pairs plus one single when their number is odd) and
+// two hole cards per opponent.  One pair costs one 16-bit draw and one table read instead of two card draws.
+//
+// Stream (a pure function of seed, stream id, sample index; shared bit for bit with the oracle):
+//   Philox block b = philox4x32_10(counter (sample lo, sample hi, stream, b), key seed); its four words are cut into
+//   eight 16-bit draws, low half first.  DEALTAB[0..1326) holds the card sets of all pairs (index C(c1,2)+c0, c0<c1),
+//   DEALTAB[1326..1378) those of the 52 single cards.
+//   * single slot (only if asked for): draws 0 and 1 of block 0 are reserved for it; a draw r is valid if r < 65520
+//     (= 1260*52) and proposes card r % 52; the first valid proposal whose card is free is taken.  If neither works
+//     (about 1 %) further draws come from blocks 0x80000000, 0x80000001, ...
+//   * pair slots, in order: draws continue after the reserved word (or from draw 0 if there is no single); r is valid
+//     if r < 64974 (= 49*1326) and proposes pair r % 1326, accepted iff both cards are free.
+//   Every accepted slot marks its cards used.  Slot roles are the caller's: hold'em uses single + first pairs = board
+//   completion, remaining pairs = opponents in order.
+constexpr int MAX_DEAL = 21;                 // cards: 5 board + 2 * 8 opponents
+constexpr int MAX_PAIR_SLOTS = 10;           // 2 board pairs + 8 opponents
+constexpr uint32_t N_PAIRS = 1326;           // C(52,2): pair index q = C(c1,2) + c0, c0 < c1
+constexpr uint32_t DEALTAB_ENTRIES = N_PAIRS + 52;
+constexpr uint32_t DEAL_PAIR_LIMIT = 49u * 1326u;    // 64,974
+constexpr uint32_t DEAL_SINGLE_LIMIT = 1260u * 52u;  // 65,520
 
-struct LocalCards {          // host / small kernels: accepted positions in a thread-local array
-    uint8_t p[MAX_DEAL];
-    PHE_HD void put(int k, uint32_t pos) { p[k] = (uint8_t)pos; }
-    PHE_HD uint32_t get(int k) const { return p[k]; }
+struct GlobalDealTab {          // host / small kernels
+    const uint64_t* t;
+    PHE_HD uint64_t mask(uint32_t q) const { return t[q]; }
 };
 
-template <class Cards>
-PHE_HD void deal_cards(uint64_t known, uint64_t seed, uint64_t sample, uint32_t stream, int need, Cards& out)
+struct LocalSlots {             // host / small kernels: accepted slots kept in thread-local storage
+    uint64_t single;
+    uint64_t pair[MAX_PAIR_SLOTS];
+    PHE_HD void put_single(uint64_t m) { single = m; }
+    PHE_HD void put_pair(int k, uint32_t, uint64_t m) { pair[k] = m; }
+    PHE_HD uint64_t get_single() const { return single; }
+    template <class DealTab>
+    PHE_HD uint64_t get_pair(int k, const DealTab&) const { return pair[k]; }
+};
+
+// returns the number of pair slots accepted (== n_pairs unless the input was malformed)
+template <class DealTab, class Slots>
+PHE_HD int deal_slots(const DealTab& dt, uint64_t known, uint64_t seed, uint64_t sample, uint32_t stream, bool want_single, int n_pairs,
+                      Slots& out)
 {
-    uint32_t used_lo = (uint32_t)known, used_hi = (uint32_t)(known >> 32);
+    uint64_t used = known;
+    const uint32_t s_lo = (uint32_t)sample, s_hi = (uint32_t)(sample >> 32), k_lo = (uint32_t)seed, k_hi = (uint32_t)(seed >> 32);
+    uint32_t rnd[4];
+    philox4x32_10(s_lo, s_hi, stream, 0u, k_lo, k_hi, rnd);
+    if (want_single) {
+        bool have = false;
+PHE_UNROLL
+        for (int h = 0; h < 2; h++) {
+            const uint32_t r = (rnd[0] >> (16 * h)) & 0xFFFFu;
+            const uint64_t m = dt.mask(N_PAIRS + r % 52u);
+            if (!have && r < DEAL_SINGLE_LIMIT && !(m & used)) { have = true; used |= m; out.put_single(m); }
+        }
+        for (uint32_t t = 0; !have && t < 64u; t++) {      // rare overflow path
+            uint32_t ex[4];
+            philox4x32_10(s_lo, s_hi, stream, 0x80000000u + t, k_lo, k_hi, ex);
+            for (int d = 0; d < 8 && !have; d++) {
+                const uint32_t r = (ex[d >> 1] >> (16 * (d & 1))) & 0xFFFFu;
+                const uint64_t m = dt.mask(N_PAIRS + r % 52u);
+                if (r < DEAL_SINGLE_LIMIT && !(m & used)) { have = true; used |= m; out.put_single(m); }
+            }
+        }
+    }
     int got = 0;
-    // 64 blocks = 1280 draws: never reached with a valid state (>= 31 of 52 cards free); bounds the loop on garbage
-    for (uint32_t blk = 0; got < need && blk < 64u; blk++) {
-        uint32_t rnd[4];
-        philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), stream, blk, (uint32_t)seed, (uint32_t)(seed >> 32), rnd);
+    int first_word = want_single ? 1 : 0;
+    // 64 blocks = 512 draws: never reached with a valid state; bounds the loop on garbage
+    for (uint32_t blk = 0; got < n_pairs && blk < 64u; blk++) {
+        if (blk) philox4x32_10(s_lo, s_hi, stream, blk, k_lo, k_hi, rnd);
 PHE_UNROLL
         for (int wi = 0; wi < 4; wi++) {
-            if (got >= need) break;
-            const uint32_t w = rnd[wi];
-            uint32_t v = w >> 10;
-            if (v >= DEAL_V_LIMIT) continue;
+            if (wi < first_word) continue;
+            if (got >= n_pairs) break;
 PHE_UNROLL
-            for (int j = 0; j < 5; j++) {
-                const uint32_t q = v / 13u;
-                const uint32_t rank = v - q * 13u;
-                v = q;
-                const uint32_t suit = (w >> (2 * j)) & 3u;
-                const uint32_t bit = 1u << (((suit & 1u) << 4) | rank);
-                const uint32_t word = (suit & 2u) ? used_hi : used_lo;
-                if (!(word & bit) && got < need) {
-                    if (suit & 2u) used_hi |= bit; else used_lo |= bit;
-                    out.put(got, (suit << 4) | rank);
+            for (int h = 0; h < 2; h++) {
+                const uint32_t r = (rnd[wi] >> (16 * h)) & 0xFFFFu;
+                const uint32_t q = r % N_PAIRS;
+                const uint64_t m = dt.mask(q);
+                if (r < DEAL_PAIR_LIMIT && !(m & used) && got < n_pairs) {
+                    used |= m;
+                    out.put_pair(got, q, m);
                     got++;
                 }
             }
         }
+        first_word = 0;
     }
+    return got;
 }
 
 // one Monte-Carlo rollout (env/workflow.py:130-148 generalised to n_opp opponents):
-// returns 0 win, 1 tie, 2 loss for the hero.  `cards` is scratch for the dealt positions.
-template <class Tab, class Cards>
-PHE_HD int mc_rollout(const Tab& tab, const HashParams& hp, uint64_t known, uint64_t hero, int nboard, int n_opp,
-                      uint64_t seed, uint64_t sample, uint32_t stream, Cards& cards)
+// returns 0 win, 1 tie, 2 loss for the hero.  `slots` is the scratch for the accepted deal slots.
+template <class Tab, class DealTab, class Slots>
+PHE_HD int mc_rollout(const Tab& tab, const HashParams& hp, const DealTab& dt, uint64_t known, uint64_t hero, int nboard, int n_opp,
+                      uint64_t seed, uint64_t sample, uint32_t stream, Slots& slots)
 {
-    const int need = (5 - nboard) + 2 * n_opp;
-    deal_cards(known, seed, sample, stream, need, cards);
+    const int nbm = 5 - nboard, nbp = nbm >> 1;
+    deal_slots(dt, known, seed, sample, stream, (nbm & 1) != 0, nbp + n_opp, slots);
     uint64_t board = known & ~hero;
-    int k = 0;
-    for (; k < 5 - nboard; k++) board |= pos_bit(cards.get(k));
+    if (nbm & 1) board |= slots.get_single();
+    for (int k = 0; k < nbp; k++) board |= slots.get_pair(k, dt);
     const uint32_t hr = eval7(board | hero, tab, hp);
     uint32_t best = 0xFFFFu;
     for (int o = 0; o < n_opp; o++) {
-        const uint64_t hole = pos_bit(cards.get(k)) | pos_bit(cards.get(k + 1));
-        k += 2;
-        const uint32_t r = eval7(board | hole, tab, hp);
+        const uint32_t r = eval7(board | slots.get_pair(nbp + o, dt), tab, hp);
         best = r < best ? r : best;
     }
     return hr < best ? 0 : (hr == best ? 1 : 2);
+}
+
+// `need` cards as ids, for phe_deal and the random step of equity plans.  Slot order = single (if need is odd), then
+// need/2 pairs; ids come out as [single, pair 0 low, pair 0 high, pair 1 low, ...], so the last two ids are always one
+// unordered pair (the villain's hand in a plan) and everything before it is an unordered group (the board completion).
+PHE_HD uint32_t lowest_pos(uint64_t m)
+{
+#ifdef __CUDA_ARCH__
+    return m ? (uint32_t)__ffsll((long long)m) - 1u : 0u;
+#else
+    return m ? (uint32_t)__builtin_ctzll(m) : 0u;
+#endif
+}
+
+template <class DealTab>
+PHE_HD void deal_ids(const DealTab& dt, uint64_t known, uint64_t seed, uint64_t sample, uint32_t stream, int need, uint8_t* ids)
+{
+    LocalSlots sl;
+    sl.single = 0;
+    for (int k = 0; k < MAX_PAIR_SLOTS; k++) sl.pair[k] = 0;
+    const int np = need >> 1, odd = need & 1;
+    deal_slots(dt, known, seed, sample, stream, odd != 0, np, sl);
+    if (odd) ids[0] = (uint8_t)pos_to_id(lowest_pos(sl.single));
+    for (int k = 0; k < np; k++) {
+        const uint64_t m = sl.pair[k];
+        ids[odd + 2 * k] = (uint8_t)pos_to_id(lowest_pos(m));
+        ids[odd + 2 * k + 1] = (uint8_t)pos_to_id(lowest_pos(m & (m - 1)));
+        if (ids[odd + 2 * k] > ids[odd + 2 * k + 1]) {
+            const uint8_t t = ids[odd + 2 * k]; ids[odd + 2 * k] = ids[odd + 2 * k + 1]; ids[odd + 2 * k + 1] = t;
+        }
+    }
 }
 
 // ---- combinations ---------------------------------------------------------------------------
@@ -269,7 +339,7 @@ struct PlanDesc {
     uint64_t n_prefix;      // product of seg_count[0 .. n_seg-2]
 };
 
-constexpr uint32_t N_PAIRS = 1326;   // C(52,2): pair index q = C(c1,2) + c0, c0 < c1
+
 
 // exist: the task's known ids (deal order).  Fills cards[n_exist .. n_exist+n_enum) with the leaf's
 // enumerated ids in visiting order.  leaf numbering = reference visiting order.

@@ -20,6 +20,7 @@ static HashParams g_hp;
 static uint32_t g_binom[53 * 8];
 static std::vector<unsigned char> g_enum_image;
 static std::vector<uint64_t> g_trimask;
+static std::vector<uint64_t> g_dealtab;
 
 extern "C" {
 
@@ -31,6 +32,8 @@ int hc_init(void)
     build_binom(g_binom);
     g_enum_image.resize(ENUM_IMG_BYTES);
     g_trimask.resize(N_TRIPLES);
+    g_dealtab.resize(DEALTAB_ENTRIES);
+    build_dealtab(g_dealtab.data());
     build_enum_image(g_enum_image.data(), g_trimask.data());
     return 0;
 }
@@ -51,9 +54,7 @@ void hc_eval7_masks(const uint64_t* m, int64_t n, uint16_t* out)
 
 void hc_deal(uint64_t known, uint64_t seed, uint64_t sample, uint32_t stream, int need, uint8_t* ids)
 {
-    LocalCards d;
-    deal_cards(known, seed, sample, stream, need, d);
-    for (int i = 0; i < need; i++) ids[i] = (uint8_t)pos_to_id(d.get(i));
+    deal_ids(GlobalDealTab{g_dealtab.data()}, known, seed, sample, stream, need, ids);
 }
 
 void hc_equity_mc(uint64_t known, uint64_t hero, int n_opp, uint64_t rollouts, uint64_t offset, uint64_t seed,
@@ -61,8 +62,9 @@ void hc_equity_mc(uint64_t known, uint64_t hero, int n_opp, uint64_t rollouts, u
 {
     GlobalTab tab{g_image.data()};
     const int nboard = __builtin_popcountll(known & ~hero);
-    LocalCards scratch;
-    for (uint64_t s = 0; s < rollouts; s++) wtl[mc_rollout(tab, g_hp, known, hero, nboard, n_opp, seed, offset + s, stream, scratch)]++;
+    LocalSlots scratch;
+    const GlobalDealTab dt{g_dealtab.data()};
+    for (uint64_t s = 0; s < rollouts; s++) wtl[mc_rollout(tab, g_hp, dt, known, hero, nboard, n_opp, seed, offset + s, stream, scratch)]++;
 }
 
 void hc_colex_unrank7(uint64_t idx, int32_t* c)
@@ -94,9 +96,7 @@ int hc_equity_plan(const uint8_t* exist, int n_exist, const int32_t* plan, int n
             uint64_t kn = known;
             for (int i = pd.n_exist; i < base; i++) kn |= id_bit(cards[i]);
             for (int j = 0; j < pd.rnd_n; j++) {
-                LocalCards d;
-                deal_cards(kn, seed, leaf * (uint64_t)pd.rnd_n + (uint64_t)j, stream, pd.rnd_k, d);
-                for (int i = 0; i < pd.rnd_k; i++) cards[base + i] = (uint8_t)pos_to_id(d.get(i));
+                deal_ids(GlobalDealTab{g_dealtab.data()}, kn, seed, leaf * (uint64_t)pd.rnd_n + (uint64_t)j, stream, pd.rnd_k, cards + base);
                 out[plan_leaf_result(tab, g_hp, cards)]++; out[3]++;
             }
         }

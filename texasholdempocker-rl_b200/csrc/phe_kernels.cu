@@ -40,7 +40,8 @@ static constexpr uint32_t kEnumBinOff = kEnumBarOff + 16;                      /
 static constexpr uint32_t kSmemEnum = kEnumBinOff + 8 * 64 * 4;
 static constexpr uint32_t kSmemTabOnly = kSmemTab + 16;
 static constexpr uint32_t kSmemPairs = kSmemTabOnly + N_PAIRS * 8;
-static constexpr uint32_t kSmemMc = kSmemTabOnly + MAX_DEAL * kCtaThreads;    // + one byte column per thread for dealt cards
+static constexpr uint32_t kDealTabBytes = DEALTAB_ENTRIES * 8;                 // 11,024
+static constexpr uint32_t kSmemMc = kSmemTabOnly + kDealTabBytes + MAX_PAIR_SLOTS * 2 * kCtaThreads;   // + deal table + slot scratch
 
 // ------------------------------------------------------------------------------------------------
 // table staging: one TMA bulk copy of the whole image, completion on an mbarrier
@@ -418,28 +419,47 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
 }
 
 // ------------------------------------------------------------------------------------------------
-// dealt-card scratch of the Monte-Carlo kernels: row k of a [MAX_DEAL][blockDim] byte matrix in shared memory
-// (threads of a warp touch 32 consecutive bytes of one row: conflict free)
-struct SmemCards {
-    uint32_t base;     // shared address of this thread's column
-    uint32_t stride;   // blockDim.x
-    __device__ __forceinline__ void put(int k, uint32_t pos) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(base + (uint32_t)k * stride), "r"(pos) : "memory"); }
-    __device__ __forceinline__ uint32_t get(int k) const
+// Monte-Carlo kernels: the deal table (pairs + singles) in shared memory and the per-thread slot scratch -- row k of a
+// [MAX_PAIR_SLOTS][blockDim] u16 matrix holds the k-th accepted pair index (threads of a warp touch 32 consecutive
+// halfwords of one row: conflict free); the single card set stays in a register.
+struct SharedDealTab {
+    uint32_t base;
+    __device__ __forceinline__ uint64_t mask(uint32_t q) const
     {
-        uint32_t v;
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)k * stride) : "memory");
+        uint64_t v;
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(base + 8u * q));
         return v;
     }
 };
 
+struct SmemSlots {
+    uint32_t base;     // shared address of this thread's halfword in row 0
+    uint32_t stride;   // bytes per row = 2 * blockDim.x
+    uint64_t single;
+    __device__ __forceinline__ void put_single(uint64_t m) { single = m; }
+    __device__ __forceinline__ void put_pair(int k, uint32_t q, uint64_t)
+    {
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + (uint32_t)k * stride), "h"((uint16_t)q) : "memory");
+    }
+    __device__ __forceinline__ uint64_t get_single() const { return single; }
+    template <class DealTab>
+    __device__ __forceinline__ uint64_t get_pair(int k, const DealTab& dt) const
+    {
+        uint16_t q;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(q) : "r"(base + (uint32_t)k * stride) : "memory");
+        return dt.mask(q);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
 // K3: Monte-Carlo equity.  One warp works on one (state, sample chunk) item at a time; lanes take
 // samples chunk_begin + lane + 32 i.  The deal is a pure function of the global sample index.
 // ------------------------------------------------------------------------------------------------
-template <class Tab>
-__device__ __forceinline__ void equity_mc_body(const Tab& tab, const ulonglong2* __restrict__ states, int64_t n_states,
+template <class Tab, class DealTab>
+__device__ __forceinline__ void equity_mc_body(const Tab& tab, const DealTab& dt, const ulonglong2* __restrict__ states, int64_t n_states,
                                                int n_opp_default, uint64_t rollouts, uint64_t sample_offset, uint64_t seed,
                                                uint32_t state_base, unsigned long long* __restrict__ wtl, uint32_t chunk,
-                                               SmemCards cards)
+                                               SmemSlots slots)
 {
     const HashParams hp = c_hp;
     const uint32_t lane = threadIdx.x & 31;
@@ -459,7 +479,7 @@ __device__ __forceinline__ void equity_mc_body(const Tab& tab, const ulonglong2*
         if (e > rollouts) e = rollouts;
         uint32_t w = 0, t = 0, l = 0;
         for (uint64_t i = b + lane; i < e; i += 32) {
-            const int res = mc_rollout(tab, hp, known, hero, nboard, n_opp, seed, sample_offset + i, state_base + (uint32_t)s, cards);
+            const int res = mc_rollout(tab, hp, dt, known, hero, nboard, n_opp, seed, sample_offset + i, state_base + (uint32_t)s, slots);
             w += (res == 0); t += (res == 1); l += (res == 2);
         }
         w = __reduce_add_sync(0xFFFFFFFFu, w);
@@ -474,33 +494,39 @@ __device__ __forceinline__ void equity_mc_body(const Tab& tab, const ulonglong2*
 }
 
 __global__ void __launch_bounds__(kCtaThreads, 1)
-k_equity_mc_smem(const uint16_t* __restrict__ g_tab, const ulonglong2* __restrict__ states, int64_t n_states, int n_opp,
-                 uint64_t rollouts, uint64_t sample_offset, uint64_t seed, uint32_t state_base,
+k_equity_mc_smem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict__ g_dealtab, const ulonglong2* __restrict__ states,
+                 int64_t n_states, int n_opp, uint64_t rollouts, uint64_t sample_offset, uint64_t seed, uint32_t state_base,
                  unsigned long long* __restrict__ wtl, uint32_t chunk)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    stage_tables(smem, g_tab, reinterpret_cast<uint64_t*>(smem + kSmemTab));
-    const SharedTab tab{(uint32_t)__cvta_generic_to_shared(smem)};
-    const SmemCards cards{(uint32_t)__cvta_generic_to_shared(smem) + kSmemTabOnly + threadIdx.x, blockDim.x};
-    equity_mc_body(tab, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk, cards);
+    uint64_t* s_deal = reinterpret_cast<uint64_t*>(smem + kSmemTabOnly);
+    for (uint32_t i = threadIdx.x; i < DEALTAB_ENTRIES; i += blockDim.x) s_deal[i] = g_dealtab[i];
+    stage_tables(smem, g_tab, reinterpret_cast<uint64_t*>(smem + kSmemTab));   // includes a __syncthreads
+    __syncthreads();
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem);
+    const SharedTab tab{sb};
+    const SharedDealTab dt{sb + kSmemTabOnly};
+    const SmemSlots slots{sb + kSmemTabOnly + kDealTabBytes + 2u * threadIdx.x, 2u * blockDim.x, 0ull};
+    equity_mc_body(tab, dt, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk, slots);
 }
 
 __global__ void __launch_bounds__(256)
-k_equity_mc_gmem(const uint16_t* __restrict__ g_tab, const ulonglong2* __restrict__ states, int64_t n_states, int n_opp,
-                 uint64_t rollouts, uint64_t sample_offset, uint64_t seed, uint32_t state_base,
+k_equity_mc_gmem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict__ g_dealtab, const ulonglong2* __restrict__ states,
+                 int64_t n_states, int n_opp, uint64_t rollouts, uint64_t sample_offset, uint64_t seed, uint32_t state_base,
                  unsigned long long* __restrict__ wtl, uint32_t chunk)
 {
-    __shared__ unsigned char s_cards[MAX_DEAL * 256];
+    __shared__ uint16_t s_slots[MAX_PAIR_SLOTS * 256];
     const GlobalTab tab{g_tab};
-    const SmemCards cards{(uint32_t)__cvta_generic_to_shared(s_cards) + threadIdx.x, blockDim.x};
-    equity_mc_body(tab, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk, cards);
+    const GlobalDealTab dt{g_dealtab};
+    const SmemSlots slots{(uint32_t)__cvta_generic_to_shared(s_slots) + 2u * threadIdx.x, 2u * blockDim.x, 0ull};
+    equity_mc_body(tab, dt, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk, slots);
 }
 
 // ------------------------------------------------------------------------------------------------
 // K3b: exact-plan equity (simulate_processes).  One thread per enumeration leaf.
 // ------------------------------------------------------------------------------------------------
 template <class Tab>
-__device__ __forceinline__ void equity_plan_body(const Tab& tab, const uint8_t* __restrict__ exist, int64_t n_tasks,
+__device__ __forceinline__ void equity_plan_body(const Tab& tab, const GlobalDealTab dt, const uint8_t* __restrict__ exist, int64_t n_tasks,
                                                  const PlanDesc& pd, uint64_t seed, uint32_t stream_base,
                                                  unsigned long long* __restrict__ wtl)
 {
@@ -525,9 +551,7 @@ __device__ __forceinline__ void equity_plan_body(const Tab& tab, const uint8_t* 
         } else {
             for (int i = pd.n_exist; i < base; i++) known |= id_bit(cards[i]);
             for (int j = 0; j < pd.rnd_n; j++) {
-                LocalCards d;
-                deal_cards(known, seed, leaf * (uint64_t)pd.rnd_n + (uint64_t)j, stream_base + (uint32_t)task, pd.rnd_k, d);
-                for (int i = 0; i < pd.rnd_k; i++) cards[base + i] = (uint8_t)pos_to_id(d.get(i));
+                deal_ids(dt, known, seed, leaf * (uint64_t)pd.rnd_n + (uint64_t)j, stream_base + (uint32_t)task, pd.rnd_k, cards + base);
                 const int res = plan_leaf_result(tab, hp, cards);
                 w += (res == 0); t += (res == 1); l += (res == 2);
             }
@@ -550,21 +574,21 @@ __device__ __forceinline__ void equity_plan_body(const Tab& tab, const uint8_t* 
 }
 
 __global__ void __launch_bounds__(kCtaThreads, 1)
-k_equity_plan_smem(const uint16_t* __restrict__ g_tab, const uint8_t* __restrict__ exist, int64_t n_tasks, PlanDesc pd, uint64_t seed,
-                   uint32_t stream_base, unsigned long long* __restrict__ wtl)
+k_equity_plan_smem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict__ g_dealtab, const uint8_t* __restrict__ exist, int64_t n_tasks,
+                   PlanDesc pd, uint64_t seed, uint32_t stream_base, unsigned long long* __restrict__ wtl)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     stage_tables(smem, g_tab, reinterpret_cast<uint64_t*>(smem + kSmemTab));
     const SharedTab tab{(uint32_t)__cvta_generic_to_shared(smem)};
-    equity_plan_body(tab, exist, n_tasks, pd, seed, stream_base, wtl);
+    equity_plan_body(tab, GlobalDealTab{g_dealtab}, exist, n_tasks, pd, seed, stream_base, wtl);
 }
 
 __global__ void __launch_bounds__(256)
-k_equity_plan_gmem(const uint16_t* __restrict__ g_tab, const uint8_t* __restrict__ exist, int64_t n_tasks, PlanDesc pd, uint64_t seed,
-                   uint32_t stream_base, unsigned long long* __restrict__ wtl)
+k_equity_plan_gmem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict__ g_dealtab, const uint8_t* __restrict__ exist, int64_t n_tasks,
+                   PlanDesc pd, uint64_t seed, uint32_t stream_base, unsigned long long* __restrict__ wtl)
 {
     const GlobalTab tab{g_tab};
-    equity_plan_body(tab, exist, n_tasks, pd, seed, stream_base, wtl);
+    equity_plan_body(tab, GlobalDealTab{g_dealtab}, exist, n_tasks, pd, seed, stream_base, wtl);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -685,14 +709,14 @@ k_showdown_gmem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict__
 // K5: determinisation deals (GameEnv.new_random, env/game.py:119-163)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_deal(const uint64_t* __restrict__ known, int64_t n, int need, uint64_t seed, uint64_t sample, uint32_t stream_base,
-       uint8_t* __restrict__ cards_out)
+k_deal(const uint64_t* __restrict__ g_dealtab, const uint64_t* __restrict__ known, int64_t n, int need, uint64_t seed, uint64_t sample,
+       uint32_t stream_base, uint8_t* __restrict__ cards_out)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    LocalCards d;
-    deal_cards(known[i] & CARD_BITS, seed, sample, stream_base + (uint32_t)i, need, d);
-    for (int k = 0; k < need; k++) cards_out[i * need + k] = (uint8_t)pos_to_id(d.get(k));
+    uint8_t ids[MAX_DEAL];
+    deal_ids(GlobalDealTab{g_dealtab}, known[i] & CARD_BITS, seed, sample, stream_base + (uint32_t)i, need, ids);
+    for (int k = 0; k < need; k++) cards_out[i * need + k] = ids[k];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -810,10 +834,10 @@ void init_device(int device)
     chk(cudaMalloc(&cx.d_counters, 2 * kCounterRing * sizeof(unsigned int)), "cudaMalloc(counters)");
     chk(cudaMemset(cx.d_counters, 0, 2 * kCounterRing * sizeof(unsigned int)), "cudaMemset(counters)");
     {
-        std::vector<uint64_t> pm(N_PAIRS);
-        build_pairmask(pm.data());
-        chk(cudaMalloc(&cx.d_pairmask, N_PAIRS * 8), "cudaMalloc(pairmask)");
-        chk(cudaMemcpy(cx.d_pairmask, pm.data(), N_PAIRS * 8, cudaMemcpyHostToDevice), "cudaMemcpy(pairmask)");
+        std::vector<uint64_t> pm(DEALTAB_ENTRIES);   // pairs, then singles; the plan fast path reads the pair prefix
+        build_dealtab(pm.data());
+        chk(cudaMalloc(&cx.d_pairmask, DEALTAB_ENTRIES * 8), "cudaMalloc(dealtab)");
+        chk(cudaMemcpy(cx.d_pairmask, pm.data(), DEALTAB_ENTRIES * 8, cudaMemcpyHostToDevice), "cudaMemcpy(dealtab)");
     }
     chk(cudaFuncSetAttribute(k_equity_plan_pairs_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPairs), "attr equity_plan_pairs");
     chk(cudaMemcpyToSymbol(c_hp, &g_hp, sizeof g_hp), "cudaMemcpyToSymbol(c_hp)");
@@ -1049,11 +1073,11 @@ int phe_equity_mc(const uint64_t* states, int64_t n_states, int n_opp, uint64_t 
     if (total < 1.0e6) {
         uint64_t blocks = (items + 7) / 8;   // 8 warps per 256-thread block
         if (blocks > (uint64_t)cx->sm_count * 8) blocks = (uint64_t)cx->sm_count * 8;
-        k_equity_mc_gmem<<<(unsigned)blocks, 256, 0, st>>>(cx->d_image, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk);
+        k_equity_mc_gmem<<<(unsigned)blocks, 256, 0, st>>>(cx->d_image, cx->d_pairmask, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk);
     } else {
         uint64_t ctas = (items + 31) / 32;
         if (ctas > (uint64_t)cx->sm_count) ctas = cx->sm_count;
-        k_equity_mc_smem<<<(unsigned)ctas, kCtaThreads, kSmemMc, st>>>(cx->d_image, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk);
+        k_equity_mc_smem<<<(unsigned)ctas, kCtaThreads, kSmemMc, st>>>(cx->d_image, cx->d_pairmask, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk);
     }
     return after_launch("equity_mc launch");
 }
@@ -1117,11 +1141,11 @@ int phe_equity_plan(const uint8_t* exist, int n_exist, int64_t n_tasks, const in
     if (deals < 2.0e6) {
         uint64_t blocks = (threads + 255) / 256;
         if (blocks > (uint64_t)cx->sm_count * 8) blocks = (uint64_t)cx->sm_count * 8;
-        k_equity_plan_gmem<<<(unsigned)blocks, 256, 0, st>>>(cx->d_image, exist, n_tasks, pd, seed, stream_base, wp);
+        k_equity_plan_gmem<<<(unsigned)blocks, 256, 0, st>>>(cx->d_image, cx->d_pairmask, exist, n_tasks, pd, seed, stream_base, wp);
     } else {
         uint64_t ctas = (threads + kCtaThreads - 1) / kCtaThreads;
         if (ctas > (uint64_t)cx->sm_count) ctas = cx->sm_count;
-        k_equity_plan_smem<<<(unsigned)ctas, kCtaThreads, kSmemTabOnly, st>>>(cx->d_image, exist, n_tasks, pd, seed, stream_base, wp);
+        k_equity_plan_smem<<<(unsigned)ctas, kCtaThreads, kSmemTabOnly, st>>>(cx->d_image, cx->d_pairmask, exist, n_tasks, pd, seed, stream_base, wp);
     }
     return after_launch("equity_plan launch");
 }
@@ -1269,7 +1293,7 @@ int phe_deal(const uint64_t* known, int64_t n, int need, uint64_t seed, uint64_t
     int rc = current_ctx(&cx);
     if (rc) return rc;
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    k_deal<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(known, n, need, seed, sample_offset, stream_base, cards_out);
+    k_deal<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(cx->d_pairmask, known, n, need, seed, sample_offset, stream_base, cards_out);
     return after_launch("deal launch");
 }
 

@@ -248,10 +248,11 @@ bool build_table_image(uint16_t* image, HashParams* hp_out)
     return false;
 }
 
-void build_pairmask(uint64_t out[N_PAIRS])
+void build_dealtab(uint64_t out[DEALTAB_ENTRIES])
 {
     for (int c1 = 1; c1 < 52; c1++)
         for (int c0 = 0; c0 < c1; c0++) out[c1 * (c1 - 1) / 2 + c0] = id_bit(c0) | id_bit(c1);
+    for (int c = 0; c < 52; c++) out[N_PAIRS + c] = id_bit(c);
 }
 
 // ---- enumeration image (phe_enum.cuh) --------------------------------------------------------

@@ -22,8 +22,8 @@ std::vector<NoflushKey> all_noflush_keys();
 // fills image[TAB_U16] and the hash multipliers; false if no perfect hash was found
 bool build_table_image(uint16_t* image, HashParams* hp_out);
 
-// card sets of all C(52,2) two-card hands, index C(c1,2) + c0
-void build_pairmask(uint64_t out[N_PAIRS]);
+// card sets of all C(52,2) two-card hands (index C(c1,2) + c0) followed by the 52 single cards (index 1326 + id)
+void build_dealtab(uint64_t out[DEALTAB_ENTRIES]);
 
 // fills image[ENUM_IMG_BYTES] and trimask[N_TRIPLES] (layouts in phe_enum.cuh)
 bool build_enum_image(unsigned char* image, uint64_t* trimask);
