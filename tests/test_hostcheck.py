@@ -123,3 +123,10 @@ def test_enum_block_walk_full(hostcheck):
     h = np.zeros(7463, dtype=np.uint64)
     hostcheck.hc_enum7(0, 133784560, vp(h))
     assert h.tolist() == json.load(open(os.path.join(GOLDEN, "hist7463.json")))["hist7463"]
+
+
+def test_multiply_shift_reductions_are_exact():
+    """phe_core.cuh mod1326_u16 / mod52_u16: exact for every 16-bit input."""
+    r = np.arange(65536, dtype=np.uint64)
+    assert ((r - (((r >> 1) * 50611) >> 25) * 1326) == r % 1326).all() and (r.max() * 50611 < 2 ** 32)
+    assert ((r - ((r * 40330) >> 21) * 52) == r % 52).all()

@@ -165,6 +165,10 @@ constexpr uint32_t DEALTAB_ENTRIES = N_PAIRS + 52;
 constexpr uint32_t DEAL_PAIR_LIMIT = 49u * 1326u;    // 64,974
 constexpr uint32_t DEAL_SINGLE_LIMIT = 1260u * 52u;  // 65,520
 
+// r % 1326 and r % 52 for r < 65536 by multiply-shift (exact for every 16-bit r; checked exhaustively in the tests)
+PHE_HD uint32_t mod1326_u16(uint32_t r) { return r - (((r >> 1) * 50611u) >> 25) * 1326u; }   // 1326 = 2 * 663
+PHE_HD uint32_t mod52_u16(uint32_t r) { return r - ((r * 40330u) >> 21) * 52u; }
+
 struct GlobalDealTab {          // host / small kernels
     const uint64_t* t;
     PHE_HD uint64_t mask(uint32_t q) const { return t[q]; }
@@ -194,7 +198,7 @@ PHE_HD int deal_slots(const DealTab& dt, uint64_t known, uint64_t seed, uint64_t
 PHE_UNROLL
         for (int h = 0; h < 2; h++) {
             const uint32_t r = (rnd[0] >> (16 * h)) & 0xFFFFu;
-            const uint64_t m = dt.mask(N_PAIRS + r % 52u);
+            const uint64_t m = dt.mask(N_PAIRS + mod52_u16(r));
             if (!have && r < DEAL_SINGLE_LIMIT && !(m & used)) { have = true; used |= m; out.put_single(m); }
         }
         for (uint32_t t = 0; !have && t < 64u; t++) {      // rare overflow path
@@ -202,7 +206,7 @@ PHE_UNROLL
             philox4x32_10(s_lo, s_hi, stream, 0x80000000u + t, k_lo, k_hi, ex);
             for (int d = 0; d < 8 && !have; d++) {
                 const uint32_t r = (ex[d >> 1] >> (16 * (d & 1))) & 0xFFFFu;
-                const uint64_t m = dt.mask(N_PAIRS + r % 52u);
+                const uint64_t m = dt.mask(N_PAIRS + mod52_u16(r));
                 if (r < DEAL_SINGLE_LIMIT && !(m & used)) { have = true; used |= m; out.put_single(m); }
             }
         }
@@ -219,7 +223,7 @@ PHE_UNROLL
 PHE_UNROLL
             for (int h = 0; h < 2; h++) {
                 const uint32_t r = (rnd[wi] >> (16 * h)) & 0xFFFFu;
-                const uint32_t q = r % N_PAIRS;
+                const uint32_t q = mod1326_u16(r);
                 const uint64_t m = dt.mask(q);
                 if (r < DEAL_PAIR_LIMIT && !(m & used) && got < n_pairs) {
                     used |= m;

@@ -41,7 +41,7 @@ static constexpr uint32_t kSmemEnum = kEnumBinOff + 8 * 64 * 4;
 static constexpr uint32_t kSmemTabOnly = kSmemTab + 16;
 static constexpr uint32_t kSmemPairs = kSmemTabOnly + N_PAIRS * 8;
 static constexpr uint32_t kDealTabBytes = DEALTAB_ENTRIES * 8;                 // 11,024
-static constexpr uint32_t kSmemMc = kSmemTabOnly + kDealTabBytes + MAX_PAIR_SLOTS * 2 * kCtaThreads;   // + deal table + slot scratch
+static constexpr uint32_t kSmemMc = kSmemTabOnly + kDealTabBytes + MAX_PAIR_SLOTS * 4 * kCtaThreads;   // + deal table + slot scratch
 
 // ------------------------------------------------------------------------------------------------
 // table staging: one TMA bulk copy of the whole image, completion on an mbarrier
@@ -420,8 +420,8 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
 
 // ------------------------------------------------------------------------------------------------
 // Monte-Carlo kernels: the deal table (pairs + singles) in shared memory and the per-thread slot scratch -- row k of a
-// [MAX_PAIR_SLOTS][blockDim] u16 matrix holds the k-th accepted pair index (threads of a warp touch 32 consecutive
-// halfwords of one row: conflict free); the single card set stays in a register.
+// [MAX_PAIR_SLOTS][blockDim] u32 matrix holds the k-th accepted pair index (threads of a warp touch 32 consecutive
+// words of one row: conflict free; 32-bit cells avoid the 16-bit conversions around the store); the single card set stays in a register.
 struct SharedDealTab {
     uint32_t base;
     __device__ __forceinline__ uint64_t mask(uint32_t q) const
@@ -433,20 +433,20 @@ struct SharedDealTab {
 };
 
 struct SmemSlots {
-    uint32_t base;     // shared address of this thread's halfword in row 0
-    uint32_t stride;   // bytes per row = 2 * blockDim.x
+    uint32_t base;     // shared address of this thread's word in row 0
+    uint32_t stride;   // bytes per row = 4 * blockDim.x
     uint64_t single;
     __device__ __forceinline__ void put_single(uint64_t m) { single = m; }
     __device__ __forceinline__ void put_pair(int k, uint32_t q, uint64_t)
     {
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + (uint32_t)k * stride), "h"((uint16_t)q) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + (uint32_t)k * stride), "r"(q) : "memory");
     }
     __device__ __forceinline__ uint64_t get_single() const { return single; }
     template <class DealTab>
     __device__ __forceinline__ uint64_t get_pair(int k, const DealTab& dt) const
     {
-        uint16_t q;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(q) : "r"(base + (uint32_t)k * stride) : "memory");
+        uint32_t q;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(q) : "r"(base + (uint32_t)k * stride) : "memory");
         return dt.mask(q);
     }
 };
@@ -506,7 +506,7 @@ k_equity_mc_smem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem);
     const SharedTab tab{sb};
     const SharedDealTab dt{sb + kSmemTabOnly};
-    const SmemSlots slots{sb + kSmemTabOnly + kDealTabBytes + 2u * threadIdx.x, 2u * blockDim.x, 0ull};
+    const SmemSlots slots{sb + kSmemTabOnly + kDealTabBytes + 4u * threadIdx.x, 4u * blockDim.x, 0ull};
     equity_mc_body(tab, dt, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk, slots);
 }
 
@@ -515,10 +515,10 @@ k_equity_mc_gmem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
                  int64_t n_states, int n_opp, uint64_t rollouts, uint64_t sample_offset, uint64_t seed, uint32_t state_base,
                  unsigned long long* __restrict__ wtl, uint32_t chunk)
 {
-    __shared__ uint16_t s_slots[MAX_PAIR_SLOTS * 256];
+    __shared__ uint32_t s_slots[MAX_PAIR_SLOTS * 256];
     const GlobalTab tab{g_tab};
     const GlobalDealTab dt{g_dealtab};
-    const SmemSlots slots{(uint32_t)__cvta_generic_to_shared(s_slots) + 2u * threadIdx.x, 2u * blockDim.x, 0ull};
+    const SmemSlots slots{(uint32_t)__cvta_generic_to_shared(s_slots) + 4u * threadIdx.x, 4u * blockDim.x, 0ull};
     equity_mc_body(tab, dt, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk, slots);
 }
 
