@@ -890,6 +890,22 @@ struct Scratch {
 };
 thread_local Scratch t_in, t_out;
 
+// Small host-buffer calls of the store-only kernels (the drop-in single-hand / single-game paths; kernels that accumulate
+// with atomics keep their outputs in device memory) skip the staging copies: the
+// arguments are memcpy'd into a per-thread pinned buffer that the kernel reads and writes through UVA, so a call is one
+// launch and one stream synchronisation.
+constexpr size_t kPinnedBytes = 64 * 1024;
+struct Pinned {
+    unsigned char* p = nullptr;
+    int get(unsigned char** out)
+    {
+        if (!p) PHE_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&p), kPinnedBytes, cudaHostAllocDefault));
+        *out = p;
+        return PHE_OK;
+    }
+};
+thread_local Pinned t_pin;
+
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
@@ -954,6 +970,16 @@ int phe_eval7_host(const void* hands, int layout, int64_t n, uint16_t* out)
     if (!hands || !out) return PHE_EINVAL;
     const size_t in_bytes = (size_t)n * (layout == PHE_LAYOUT_IDS ? 7 : 8);
     int rc;
+    if (align256(in_bytes) + (size_t)n * 2 <= kPinnedBytes) {
+        unsigned char* pin;
+        if ((rc = t_pin.get(&pin))) return rc;
+        std::memcpy(pin, hands, in_bytes);
+        uint16_t* res = reinterpret_cast<uint16_t*>(pin + align256(in_bytes));
+        if ((rc = phe_eval7(pin, layout, n, res, nullptr))) return rc;
+        PHE_CUDA(cudaStreamSynchronize(0));
+        std::memcpy(out, res, (size_t)n * 2);
+        return PHE_OK;
+    }
     if ((rc = t_in.ensure(in_bytes)) || (rc = t_out.ensure((size_t)n * 2))) return rc;
     PHE_CUDA(cudaMemcpyAsync(t_in.p, hands, in_bytes, cudaMemcpyHostToDevice, 0));
     if ((rc = phe_eval7(t_in.p, layout, n, static_cast<uint16_t*>(t_out.p), nullptr))) return rc;
@@ -1206,6 +1232,22 @@ int phe_showdown_host(const uint64_t* boards, const uint64_t* holes, const uint3
     const size_t in_bytes = o_live + align256(G * 4);
     const size_t o_win = 0, o_ranks = align256(G * 4), out_bytes = o_ranks + align256(G * P * 2);
     int rc;
+    if (in_bytes + out_bytes <= kPinnedBytes) {
+        unsigned char* pin;
+        if ((rc = t_pin.get(&pin))) return rc;
+        std::memcpy(pin + o_boards, boards, G * 8);
+        std::memcpy(pin + o_holes, holes, G * P * 8);
+        if (live) std::memcpy(pin + o_live, live, G * 4);
+        unsigned char* po = pin + in_bytes;
+        if ((rc = phe_showdown(reinterpret_cast<uint64_t*>(pin + o_boards), reinterpret_cast<uint64_t*>(pin + o_holes),
+                               live ? reinterpret_cast<uint32_t*>(pin + o_live) : nullptr, n_games, n_players,
+                               reinterpret_cast<uint32_t*>(po + o_win), ranks_out ? reinterpret_cast<uint16_t*>(po + o_ranks) : nullptr, nullptr)))
+            return rc;
+        PHE_CUDA(cudaStreamSynchronize(0));
+        std::memcpy(winners_out, po + o_win, G * 4);
+        if (ranks_out) std::memcpy(ranks_out, po + o_ranks, G * P * 2);
+        return PHE_OK;
+    }
     if ((rc = t_in.ensure(in_bytes)) || (rc = t_out.ensure(out_bytes))) return rc;
     char* di = static_cast<char*>(t_in.p);
     char* dout = static_cast<char*>(t_out.p);
