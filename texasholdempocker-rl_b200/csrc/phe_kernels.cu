@@ -549,11 +549,23 @@ __device__ __forceinline__ void equity_plan_body(const Tab& tab, const GlobalDea
             const int res = plan_leaf_result(tab, hp, cards);
             w = (res == 0); t = (res == 1); l = (res == 2);
         } else {
+            // random step (env/workflow.py:181-195): rnd_k cards = the board cards still missing + the villain's two.
+            // Slots: [single if the missing board count is odd][board pairs][villain pair]; card sets are used directly
+            // and the hero is ranked once per leaf when the enumeration has already completed the board.
             for (int i = pd.n_exist; i < base; i++) known |= id_bit(cards[i]);
+            const uint64_t hero = id_bit(cards[0]) | id_bit(cards[1]);
+            const uint64_t board0 = known & ~hero;
+            const int nbm = pd.rnd_k - 2, nbp = nbm >> 1;
+            const uint32_t hr0 = nbm == 0 ? eval7(board0 | hero, tab, hp) : 0u;
+            LocalSlots sl;
             for (int j = 0; j < pd.rnd_n; j++) {
-                deal_ids(dt, known, seed, leaf * (uint64_t)pd.rnd_n + (uint64_t)j, stream_base + (uint32_t)task, pd.rnd_k, cards + base);
-                const int res = plan_leaf_result(tab, hp, cards);
-                w += (res == 0); t += (res == 1); l += (res == 2);
+                deal_slots(dt, known, seed, leaf * (uint64_t)pd.rnd_n + (uint64_t)j, stream_base + (uint32_t)task, (nbm & 1) != 0, nbp + 1, sl);
+                uint64_t board = board0;
+                if (nbm & 1) board |= sl.single;
+                for (int k = 0; k < nbp; k++) board |= sl.pair[k];
+                const uint32_t hr = nbm == 0 ? hr0 : eval7(board | hero, tab, hp);
+                const uint32_t vr = eval7(board | sl.pair[nbp], tab, hp);
+                w += hr < vr; t += hr == vr; l += hr > vr;
             }
         }
         // aggregate lanes that work on the same task before touching global memory
