@@ -10,7 +10,7 @@ Python surface (mirrors the reference where one exists):
 """
 from . import _native
 from .cardset import DECK, Card, CardDecor, CardFigure, card_id, card_to_evaluator, cards_to_mask, ids_to_masks, mask_to_ids
-from .equity import deal, equity_mc, equity_plan, pack_states, plan_num_deals, random_states, showdown, win_probability
+from .equity import deal, determinise, equity_mc, equity_plan, pack_states, plan_num_deals, random_states, showdown, win_probability
 from .evaluator import enumerate_c52_7, eval7, evaluate_cards
 from .service import simulate_processes, solve_tasks, winning_probability
 from .settlement import settle, settle_env, settle_envs
@@ -19,7 +19,7 @@ from .winner import GameEnv, GamePlayerResult, winner_sets
 
 __all__ = [
     "DECK", "Card", "CardDecor", "CardFigure", "card_id", "card_to_evaluator", "cards_to_mask", "ids_to_masks", "mask_to_ids",
-    "deal", "equity_mc", "equity_plan", "pack_states", "plan_num_deals", "random_states", "showdown", "win_probability",
+    "deal", "determinise", "equity_mc", "equity_plan", "pack_states", "plan_num_deals", "random_states", "showdown", "win_probability",
     "enumerate_c52_7", "eval7", "evaluate_cards", "simulate_processes", "solve_tasks", "winning_probability",
     "settle", "settle_env", "settle_envs", "FusedEnum7", "shard_range", "sharded_enum7", "sharded_equity_mc", "GameEnv", "GamePlayerResult", "winner_sets",
 ]

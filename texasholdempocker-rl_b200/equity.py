@@ -209,3 +209,34 @@ def win_probability(wtl):
     w = np.asarray(wtl.cpu() if _is_cuda_tensor(wtl) else wtl, dtype=np.float64)
     n = w.sum(-1)
     return ((w[..., 0] - w[..., 2]) / n) * 0.5 + 0.5
+
+
+def determinise(hero_cards, board_cards, n_players, n, seed, sample_offset=0, stream=0):
+    """Batched GameEnv.new_random() (env/game.py:119-163): `n` uniform re-deals of everything the acting player cannot see.
+
+    hero_cards: the acting player's two cards; board_cards: the revealed board (0, 3, 4 or 5 cards); n_players: seats
+    at the table.  Returns (opp_holes uint8[n, n_players-1, 2] with each hand sorted as the reference sorts it,
+    board uint8[n, 5] = revealed cards followed by the newly dealt ones, the dealt flop part sorted).  Re-deal i uses
+    sample index sample_offset + i of stream `stream`; results are numpy arrays (host).
+    """
+    hero = [card_id(c) for c in hero_cards]
+    shown = [card_id(c) for c in (board_cards or [])]
+    if len(hero) != 2 or len(shown) not in (0, 3, 4, 5) or len(set(hero + shown)) != len(hero) + len(shown):
+        raise ValueError("need two hole cards and 0, 3, 4 or 5 distinct board cards")
+    n_opp = int(n_players) - 1
+    nbm = 5 - len(shown)
+    need = 2 * n_opp + nbm
+    if not 1 <= n_opp <= 8 or need > 21:
+        raise ValueError("1..8 opponents")
+    known = np.full(int(n), cards_to_mask(hero + shown), dtype=np.int64)
+    # one deal per re-deal: stream id fixed, sample index = re-deal number -> phe_deal's per-row stream is its row index,
+    # so rows are made distinct through stream_base = stream and sample_offset; each row i uses stream (stream + i).
+    ids = deal(known, need, seed, sample_offset=sample_offset, stream_base=stream)
+    odd = need & 1
+    # slot order of phe_deal: [single if need is odd][pairs ...]; opponents take the first pairs, the board the rest
+    opp = np.sort(ids[:, odd:odd + 2 * n_opp].reshape(n, n_opp, 2), axis=2)
+    rest = np.concatenate([ids[:, :odd], ids[:, odd + 2 * n_opp:]], axis=1)
+    if nbm == 5:
+        rest = np.concatenate([np.sort(rest[:, :3], axis=1), rest[:, 3:]], axis=1)   # the reference sorts a new flop
+    board = np.concatenate([np.tile(np.array(shown, dtype=np.uint8), (n, 1)).reshape(n, len(shown)), rest.astype(np.uint8)], axis=1)
+    return opp.astype(np.uint8), board
