@@ -345,7 +345,10 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
             const uint32_t s3lo = (uint32_t)b.s3, s3hi = (uint32_t)(b.s3 >> 32), kbias = b.kbias;
             // warp-uniform trip counts; kU hands per lane per trip keep kU independent LDS -> (LDG) -> LDS -> ATOMS
             // chains in flight, which is what hides the L2 round trip of the flush path
-            constexpr int kU = 4;
+#ifndef PHE_ENUM_KU
+#define PHE_ENUM_KU 4
+#endif
+            constexpr int kU = PHE_ENUM_KU;
             uint32_t tb = t_start;
             for (; tb + 32 * kU <= stop; tb += 32 * kU) {
                 const uint32_t t0 = tb + lane;
@@ -1014,7 +1017,10 @@ static int launch_enum7(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin
     // 512 hands (per-tile unranking and partial blocks) nor more than 2048 (tail balance)
     uint64_t tile = total / ((uint64_t)nparts * cx->sm_count * (kCtaThreads / 32) * 8);
     if (tile < 512) tile = 512;
-    if (tile > 2048) tile = 2048;
+#ifndef PHE_ENUM_TILE_MAX
+#define PHE_ENUM_TILE_MAX 2048
+#endif
+    if (tile > PHE_ENUM_TILE_MAX) tile = PHE_ENUM_TILE_MAX;
     tile &= ~(uint64_t)3;
     // graded tiling (see k_enum7): sizes 64, 68, 72, ... up to `tile`, then constant
     const uint64_t t0 = (tile - 64) / 4, s0 = 64 * t0 + (t0 ? 2 * t0 * (t0 - 1) : 0);
