@@ -126,3 +126,35 @@ def test_gpu_service_returns_reference_tuples(phe):
         got[r[0]] = r
     for i, t in exact:
         assert got[i] == (i, "p", t["round"], t["default"]["n"], t["default"]["sum"])
+
+
+# ---- unusual plan shapes, run through the reference's own simulate_processes (tests/golden/make_plan_golden.py) ----
+PLAN_GOLD = json.load(open(os.path.join(GOLDEN, "plan_run.json")))
+
+
+def _check_custom_plans(solver, num_deals):
+    for t in PLAN_GOLD:
+        plan = [tuple(r) for r in t["plan"]]
+        assert num_deals(len(t["ids"]), plan) == t["n"]
+        w, ti, l = solver(t["ids"], plan)
+        assert w + ti + l == t["n"]
+        if all(r[0] == 1 for r in plan):
+            assert float(w - l) == t["sum"], t            # exhaustive, any segmentation: exact
+        else:
+            assert abs((w - l) - t["sum"]) / t["n"] <= 4 * (2.0 / t["n"]) ** 0.5, t
+
+
+def test_oracle_matches_reference_on_custom_plans(oracle):
+    _check_custom_plans(lambda ids, plan: oracle.equity_plan(ids, plan, seed=3)[:3],
+                        lambda n_exist, plan: oracle.equity_plan(list(range(n_exist)), plan)[3])
+
+
+def test_plan_parser_counts_match_reference_on_custom_plans(phe):
+    for t in PLAN_GOLD:
+        assert phe.plan_num_deals(len(t["ids"]), [tuple(r) for r in t["plan"]]) == t["n"]
+
+
+@pytest.mark.gpu
+def test_gpu_matches_reference_on_custom_plans(phe):
+    _check_custom_plans(lambda ids, plan: tuple(int(x) for x in phe.equity_plan(np.array([ids], dtype=np.uint8), plan, seed=3)[0]),
+                        phe.plan_num_deals)
