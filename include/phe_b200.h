@@ -145,7 +145,9 @@ int phe_showdown_host(const uint64_t *boards, const uint64_t *holes, const uint3
 /* For each of n deals: draw `need` (1..21) distinct cards uniformly from the cards not
  * in known[i] (same Philox stream as phe_equity_mc: stream id
  * stream_base + i, sample index sample_offset) and write their ids to
- * cards_out[i*need ..]. */
+ * cards_out[i*need ..]: the single card first when `need` is odd, then need/2
+ * unordered pairs, each as (lower id, higher id).  Any value-independent
+ * assignment of these slots to roles is a uniform deal. */
 int phe_deal(const uint64_t *known, int64_t n, int need, uint64_t seed, uint64_t sample_offset,
              uint32_t stream_base, uint8_t *cards_out, void *stream);
 int phe_deal_host(const uint64_t *known, int64_t n, int need, uint64_t seed, uint64_t sample_offset,
