@@ -38,6 +38,11 @@ constexpr uint32_t TAB_BYTES = TAB_U16 * 2;
 
 // multipliers of the two hash functions (found by the table builder, verified collision free)
 struct HashParams { uint32_t a1, b1, a2, b2; };
+// Range reductions are multiply-high (umulhi(h, n), Lemire) so that they run on the FMA pipe: the kernels are bound by
+// the logic (alu) pipe.  Ranges that are not powers of two keep the compiler from turning them back into shifts.
+constexpr uint32_t HASH_BUCKETS = 8191;        // bucket = umulhi(h1, 8191) in [0, 8191)
+constexpr uint32_t HASH_DISP_MUL = 0x9E3779B1u; // slot = (h2 + DISP[bucket] * HASH_DISP_MUL) >> 16: the displacement re-seeds
+                                                // the second hash, so no wrap-around mask is needed
 
 constexpr uint64_t CARD_BITS = 0x1FFF1FFF1FFF1FFFull;
 
@@ -103,12 +108,12 @@ PHE_HD uint32_t eval7(uint64_t m, const Tab& tab, const HashParams& hp)
     const uint32_t b0 = x ^ x1;                       // low 16 bits valid
     const uint32_t cy = x & x1;
     const uint32_t b1 = a ^ a1 ^ cy;
-    const uint32_t b2 = ((a & a1) | (a & cy) | (a1 & cy)) & 0xFFFFu;
+    const uint32_t b2 = (a & a1) | (a & cy) | (a1 & cy);   // a1 and cy have clean upper halves, so has b2
     const uint32_t key = (b0 & 0xFFFFu) | (b1 << 16);
     const uint32_t h1 = key * hp.a1 + b2 * hp.b1;
     const uint32_t h2 = key * hp.a2 + b2 * hp.b2;
-    const uint32_t d = tab.ld(OFF_DISP + (h1 >> 19));
-    const uint32_t inf = ((h2 >> 16) + d) & 0xFFFFu;
+    const uint32_t d = tab.ld(OFF_DISP + umulhi32(h1, HASH_BUCKETS));
+    const uint32_t inf = (h2 + d * HASH_DISP_MUL) >> 16;
     // flush: with 7 cards at most one suit lane holds >= 5
     const int plo = popc32(lo);
     const uint32_t w = plo >= 5 ? lo : hi;

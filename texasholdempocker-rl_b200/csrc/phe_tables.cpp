@@ -176,25 +176,25 @@ std::vector<NoflushKey> all_noflush_keys()
 
 static inline uint32_t key_of(const NoflushKey& k) { return (k.b0 & 0xFFFFu) | (k.b1 << 16); }
 
-// hash-and-displace: bucket = h1 >> 19, slot = ((h2 >> 16) + DISP[bucket]) & 0xFFFF
+// hash-and-displace: bucket = umulhi(h1, HASH_BUCKETS); slot = (h2 + DISP[bucket] * HASH_DISP_MUL) >> 16
 static bool try_build(const std::vector<NoflushKey>& keys, const HashParams& hp, uint16_t* image)
 {
     const size_t n = keys.size();
-    std::vector<uint32_t> bucket(n), pos(n);
+    std::vector<uint32_t> bucket(n), h2(n);
     for (size_t i = 0; i < n; i++) {
         const uint32_t key = key_of(keys[i]);
-        bucket[i] = (key * hp.a1 + keys[i].b2 * hp.b1) >> 19;
-        pos[i] = (key * hp.a2 + keys[i].b2 * hp.b2) >> 16;
+        bucket[i] = umulhi32(key * hp.a1 + keys[i].b2 * hp.b1, HASH_BUCKETS);
+        h2[i] = key * hp.a2 + keys[i].b2 * hp.b2;
+    }
+    // the pair (bucket, h2) must identify a key
+    {
+        std::vector<uint64_t> id(n);
+        for (size_t i = 0; i < n; i++) id[i] = ((uint64_t)bucket[i] << 32) | h2[i];
+        std::sort(id.begin(), id.end());
+        if (std::adjacent_find(id.begin(), id.end()) != id.end()) return false;
     }
     std::vector<std::vector<uint32_t>> members(DISP_SIZE);
     for (size_t i = 0; i < n; i++) members[bucket[i]].push_back((uint32_t)i);
-    // two keys of one bucket must not share a slot offset
-    for (auto& mb : members) {
-        std::vector<uint32_t> p;
-        for (uint32_t i : mb) p.push_back(pos[i]);
-        std::sort(p.begin(), p.end());
-        if (std::adjacent_find(p.begin(), p.end()) != p.end()) return false;
-    }
     std::vector<uint32_t> order(DISP_SIZE);
     for (uint32_t b = 0; b < DISP_SIZE; b++) order[b] = b;
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return members[x].size() > members[y].size(); });
@@ -203,17 +203,24 @@ static bool try_build(const std::vector<NoflushKey>& keys, const HashParams& hp,
     uint16_t* disp = image + OFF_DISP;
     std::memset(noflush, 0, NOFLUSH_SIZE * sizeof(uint16_t));
     std::memset(disp, 0, DISP_SIZE * sizeof(uint16_t));
+    std::vector<uint32_t> slots;
     for (uint32_t b : order) {
         const auto& mb = members[b];
         if (mb.empty()) break;
         bool placed = false;
-        for (uint32_t d = 0; d < NOFLUSH_SIZE && !placed; d++) {
+        for (uint32_t d = 0; d < 65536u && !placed; d++) {
+            slots.clear();
             bool ok = true;
-            for (uint32_t i : mb)
-                if (taken[(pos[i] + d) & 0xFFFFu]) { ok = false; break; }
-            if (!ok) continue;
             for (uint32_t i : mb) {
-                const uint32_t s = (pos[i] + d) & 0xFFFFu;
+                const uint32_t s = (h2[i] + d * HASH_DISP_MUL) >> 16;
+                if (taken[s]) { ok = false; break; }
+                slots.push_back(s);
+            }
+            if (!ok) continue;
+            std::sort(slots.begin(), slots.end());
+            if (std::adjacent_find(slots.begin(), slots.end()) != slots.end()) continue;
+            for (uint32_t i : mb) {
+                const uint32_t s = (h2[i] + d * HASH_DISP_MUL) >> 16;
                 taken[s] = 1;
                 noflush[s] = keys[i].rank;
             }
