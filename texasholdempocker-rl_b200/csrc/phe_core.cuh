@@ -36,8 +36,10 @@ constexpr uint32_t OFF_FLUSH = NOFLUSH_SIZE + DISP_SIZE;
 constexpr uint32_t TAB_U16 = NOFLUSH_SIZE + DISP_SIZE + FLUSH_SIZE;   // 81920 -> 163,840 bytes
 constexpr uint32_t TAB_BYTES = TAB_U16 * 2;
 
-// multipliers of the two hash functions (found by the table builder, verified collision free)
-struct HashParams { uint32_t a1, b1, a2, b2; };
+// multipliers of the two hash functions (found by the table builder, verified collision free).  `two` is the constant 2,
+// kept where the compiler cannot see it: table byte addresses are formed as idx * two + base, one IMAD on the FMA pipe
+// instead of a LEA / IADD3 on the logic pipe that bounds these kernels.
+struct HashParams { uint32_t a1, b1, a2, b2, two; };
 // Range reductions are multiply-high (umulhi(h, n), Lemire) so that they run on the FMA pipe: the kernels are bound by
 // the logic (alu) pipe.  Ranges that are not powers of two keep the compiler from turning them back into shifts.
 constexpr uint32_t HASH_BUCKETS = 8191;        // bucket = umulhi(h1, 8191) in [0, 8191)
@@ -81,19 +83,62 @@ struct GlobalTab {
         return p[idx];
 #endif
     }
+    PHE_HD uint32_t ld_disp(uint32_t bucket, const HashParams&) const { return ld(OFF_DISP + bucket); }
+    // the single final read: FLUSH[lane] for a flush, NOFLUSH[slot] otherwise
+    PHE_HD uint32_t ld_rank(bool fl, uint32_t lane, uint32_t slot, const HashParams&) const { return ld(fl ? OFF_FLUSH + lane : slot); }
 };
 
 #ifdef __CUDACC__
 struct SharedTab {
     uint32_t base;   // shared-window byte address of the table image
-    __device__ __forceinline__ uint32_t ld(uint32_t idx) const
+    __device__ __forceinline__ uint32_t lds(uint32_t a) const
     {
         uint16_t v;
-        asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(base + idx * 2u));
+        asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
         return v;
+    }
+    __device__ __forceinline__ uint32_t ld(uint32_t idx) const { return lds(base + idx * 2u); }
+    __device__ __forceinline__ uint32_t ld_disp(uint32_t bucket, const HashParams& hp) const { return lds(bucket * hp.two + (base + 2u * OFF_DISP)); }
+    __device__ __forceinline__ uint32_t ld_rank(bool fl, uint32_t lane, uint32_t slot, const HashParams& hp) const
+    {
+        const uint32_t af = lane * hp.two + (base + 2u * OFF_FLUSH), an = slot * hp.two + base;
+        return lds(fl ? af : an);
     }
 };
 #endif
+
+// (p ^ q) & 0xFFFF, p ^ q ^ r and majority(p, q, r) as single LOP3s: left to itself the compiler re-associates the
+// bit-sliced adder below into 10 logic ops instead of 8
+PHE_HD uint32_t xor_low16(uint32_t p, uint32_t q)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, 0xFFFF, 0x28;" : "=r"(r) : "r"(p), "r"(q));
+    return r;
+#else
+    return (p ^ q) & 0xFFFFu;
+#endif
+}
+PHE_HD uint32_t xor3(uint32_t p, uint32_t q, uint32_t r)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t o;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(o) : "r"(p), "r"(q), "r"(r));
+    return o;
+#else
+    return p ^ q ^ r;
+#endif
+}
+PHE_HD uint32_t maj3(uint32_t p, uint32_t q, uint32_t r)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t o;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(o) : "r"(p), "r"(q), "r"(r));
+    return o;
+#else
+    return (p & q) | (p & r) | (q & r);
+#endif
+}
 
 // ---- 7-card evaluator on a card-set word -----------------------------------------------------
 // m must have exactly 7 card bits set.  Branch free: the flush and the non-flush index are both
@@ -105,14 +150,14 @@ PHE_HD uint32_t eval7(uint64_t m, const Tab& tab, const HashParams& hp)
     // rank multiplicities, bit sliced: count(r) = b0 + 2*b1 + 4*b2
     const uint32_t x = lo ^ hi, a = lo & hi;
     const uint32_t x1 = x >> 16, a1 = a >> 16;
-    const uint32_t b0 = x ^ x1;                       // low 16 bits valid
+    const uint32_t b0 = xor_low16(x, x1);
     const uint32_t cy = x & x1;
-    const uint32_t b1 = a ^ a1 ^ cy;
-    const uint32_t b2 = (a & a1) | (a & cy) | (a1 & cy);   // a1 and cy have clean upper halves, so has b2
-    const uint32_t key = (b0 & 0xFFFFu) | (b1 << 16);
+    const uint32_t b1 = xor3(a, a1, cy);               // upper half is garbage, shifted out below
+    const uint32_t b2 = maj3(a, a1, cy);               // a1 and cy have clean upper halves, so has b2
+    const uint32_t key = b1 * 65536u + b0;
     const uint32_t h1 = key * hp.a1 + b2 * hp.b1;
     const uint32_t h2 = key * hp.a2 + b2 * hp.b2;
-    const uint32_t d = tab.ld(OFF_DISP + umulhi32(h1, HASH_BUCKETS));
+    const uint32_t d = tab.ld_disp(umulhi32(h1, HASH_BUCKETS), hp);
     const uint32_t inf = (h2 + d * HASH_DISP_MUL) >> 16;
     // flush: with 7 cards at most one suit lane holds >= 5
     const int plo = popc32(lo);
@@ -121,7 +166,7 @@ PHE_HD uint32_t eval7(uint64_t m, const Tab& tab, const HashParams& hp)
     const int pl = popc32(wl), pw = popc32(w);
     const uint32_t lane = pl >= 5 ? wl : (w >> 16);
     const bool fl = (pl >= 5) | (pw - pl >= 5);
-    return tab.ld(fl ? OFF_FLUSH + lane : inf);
+    return tab.ld_rank(fl, lane, inf, hp);
 }
 
 PHE_HD int category_of(uint32_t rank)

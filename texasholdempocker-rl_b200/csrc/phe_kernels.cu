@@ -120,6 +120,13 @@ __device__ __forceinline__ uint64_t hand_from_ids(const uint8_t* p)
 // ------------------------------------------------------------------------------------------------
 // K1: batched eval7 (evaluate_cards, env/game.py:675)
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: the kernel is launched with programmaticStreamSerialization, so in a stream of batches
+// its CTAs become resident as the previous grid's CTAs retire and stage the table image while that grid drains;
+// griddepcontrol.wait (a no-op without a programmatic predecessor) orders every access to caller memory after the
+// previous grid has completed.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 template <int LAYOUT>
 __global__ void __launch_bounds__(kCtaThreads, 1)
 k_eval7_smem(const uint16_t* __restrict__ g_tab, const void* __restrict__ hands, int64_t n, uint16_t* __restrict__ out)
@@ -130,23 +137,34 @@ k_eval7_smem(const uint16_t* __restrict__ g_tab, const void* __restrict__ hands,
     const HashParams hp = c_hp;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    grid_dependency_wait();
     if (LAYOUT == PHE_LAYOUT_MASKS) {
         const uint64_t* h = static_cast<const uint64_t*>(hands);
         const bool vec = ((reinterpret_cast<uintptr_t>(h) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
         const int64_t n4 = vec ? (n >> 2) : 0;
-        // four hands per thread per trip: two 128-bit loads, one 64-bit store
-        for (int64_t q = gtid; q < n4; q += nthr) {
-            const ulonglong2 v0 = __ldcs(reinterpret_cast<const ulonglong2*>(h) + 2 * q);
-            const ulonglong2 v1 = __ldcs(reinterpret_cast<const ulonglong2*>(h) + 2 * q + 1);
+        const ulonglong2* hv = reinterpret_cast<const ulonglong2*>(h);
+        // four hands per thread per trip: two 128-bit loads, one 64-bit store.  The loads of trip i+1 are issued before
+        // trip i is evaluated (one CTA of 1024 threads per SM holds only 32 KB in flight per trip: not enough to cover
+        // the HBM latency at full bandwidth).
+        int64_t q = gtid;
+        ulonglong2 v0 = make_ulonglong2(0, 0), v1 = v0;
+        if (q < n4) { v0 = __ldcs(hv + 2 * q); v1 = __ldcs(hv + 2 * q + 1); }
+        grid_launch_dependents();
+        for (; q < n4; q += nthr) {
+            const int64_t qn = q + nthr;
+            ulonglong2 w0 = v0, w1 = v1;
+            if (qn < n4) { w0 = __ldcs(hv + 2 * qn); w1 = __ldcs(hv + 2 * qn + 1); }
             const uint32_t r0 = eval7(v0.x, tab, hp), r1 = eval7(v0.y, tab, hp);
             const uint32_t r2 = eval7(v1.x, tab, hp), r3 = eval7(v1.y, tab, hp);
             uint2 o;
             o.x = r0 | (r1 << 16);
             o.y = r2 | (r3 << 16);
             __stcs(reinterpret_cast<uint2*>(out) + q, o);
+            v0 = w0; v1 = w1;
         }
         for (int64_t i = n4 * 4 + gtid; i < n; i += nthr) out[i] = (uint16_t)eval7(ld_nc_u64(h + i), tab, hp);
     } else {
+        grid_launch_dependents();
         const uint8_t* h = static_cast<const uint8_t*>(hands);
         for (int64_t i = gtid; i < n; i += nthr) out[i] = (uint16_t)eval7(hand_from_ids(h + 7 * i), tab, hp);
     }
@@ -972,8 +990,21 @@ int phe_eval7(const void* hands, int layout, int64_t n, uint16_t* out, void* str
         if (layout == PHE_LAYOUT_IDS) k_eval7_gmem<PHE_LAYOUT_IDS><<<blocks, 256, 0, st>>>(cx->d_image, hands, n, out);
         else k_eval7_gmem<PHE_LAYOUT_MASKS><<<blocks, 256, 0, st>>>(cx->d_image, hands, n, out);
     } else {
-        if (layout == PHE_LAYOUT_IDS) k_eval7_smem<PHE_LAYOUT_IDS><<<cx->sm_count, kCtaThreads, kSmemTabOnly, st>>>(cx->d_image, hands, n, out);
-        else k_eval7_smem<PHE_LAYOUT_MASKS><<<cx->sm_count, kCtaThreads, kSmemTabOnly, st>>>(cx->d_image, hands, n, out);
+        // programmatic dependent launch (see k_eval7_smem): overlaps this grid's table staging with the previous grid's tail
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)cx->sm_count);
+        cfg.blockDim = dim3(kCtaThreads);
+        cfg.dynamicSmemBytes = kSmemTabOnly;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        const uint16_t* img = cx->d_image;
+        cudaError_t e = layout == PHE_LAYOUT_IDS ? cudaLaunchKernelEx(&cfg, k_eval7_smem<PHE_LAYOUT_IDS>, img, hands, n, out)
+                                                 : cudaLaunchKernelEx(&cfg, k_eval7_smem<PHE_LAYOUT_MASKS>, img, hands, n, out);
+        if (e != cudaSuccess) return cuda_fail(e, "eval7 launch");
     }
     return after_launch("eval7 launch");
 }
