@@ -168,6 +168,24 @@ int phe_settle_host(const uint64_t *boards, const uint64_t *holes, const int8_t 
                     int n_players, int max_rounds, int small_blind, int32_t *won_out, int8_t *result_out,
                     int8_t *card_result_out, uint32_t *paid_out);
 
+/* ---- policy / value network glue (PolicyValueNet: rl/models.py:12-115, 402-481) ---------------------------- */
+#define PHE_DTYPE_F32   0
+#define PHE_DTYPE_BF16  1
+/* out[r] = LayerNorm(x[r] + residual[r]) * gamma + beta over rows of d contiguous elements (residual may be NULL);
+ * the post-LN steps of nn.TransformerEncoderLayer as built at rl/models.py:446-447.  Statistics in fp32, biased
+ * variance, eps inside the square root.  Pointers 16-byte aligned, d a multiple of 16 bytes, d <= 2048 (bf16) /
+ * 1024 (f32). */
+int phe_nn_add_layernorm(const void *x, const void *residual, const void *gamma, const void *beta, void *out,
+                         int64_t rows, int d, float eps, int dtype, void *stream);
+/* Encoder input of EnvEmbedding.forward (rl/models.py:100-114) with the sqrt(d_model) scaling of rl/models.py:462-466
+ * folded into the tables: out[b][s] = starters[s] for s < n_starters, else
+ * field_tab[obs[b][f] + field_start[f]] (de elements) followed by pos_tab[f] (dp elements), f = s - n_starters.
+ * obs int32[batch][n_fields]; out [batch][n_starters + n_fields][de + dp].  Table indices are clamped to
+ * [0, n_rows) for memory safety only. */
+int phe_nn_embed_obs(const int32_t *obs, const int32_t *field_start, const void *field_tab, const void *pos_tab,
+                     const void *starters, void *out, int64_t batch, int n_fields, int n_starters, int de, int dp,
+                     int n_rows, int dtype, void *stream);
+
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
 uint64_t phe_launch_count(void);
 

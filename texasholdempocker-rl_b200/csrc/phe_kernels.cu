@@ -943,6 +943,9 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
+// launch accounting for the other translation units of the library (phe_nn.cu)
+void phe_internal_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 extern "C" {
 
 const char* phe_strerror(int status)
