@@ -337,6 +337,37 @@ def main():
                                         "config": {"workload": "reference task tuples (env/env.py:240) -> result tuples (env/workflow.py:225), default plans, 128 games"},
                                         "cpu_python_port": {"value": pdeals / pdt, "unit": "deals/s", "cores": 1,
                                                             "sample": f"{pdeals} deals of river tasks through oracle/pyport.run_plan"}}
+            # --- policy / value leaf inference: default.yml model, 1024 observations per call, bf16 ---
+            pv = phe.policy_value
+            net = pv.fill_parameters(pv.PolicyValueNet(**pv.DEFAULT_MODEL_PARAMS), 1)
+            pred = pv.BatchedPredictor(net, dtype=torch.bfloat16, max_batch=1024, buckets=[1, 1024])
+            pred.warmup()
+            obs = pv.random_observations(1024, seed=5)
+            dobs = torch.from_numpy(obs).to(dev)
+            pred.predict_batch(dobs)
+            torch.cuda.synchronize()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(10):
+                pred.predict_batch(dobs)
+            p1.record()
+            torch.cuda.synchronize()
+            pms = p0.elapsed_time(p1) / 10
+            t0 = time.perf_counter()
+            for _ in range(10):
+                probs, val = pred.predict_batch(obs)              # numpy in, numpy out: pinned H2D + graph replay + D2H
+            pe2e = (time.perf_counter() - t0) / 10
+            t0 = time.perf_counter()
+            for _ in range(50):
+                pred.predict(obs[0])
+            p1lat = (time.perf_counter() - t0) / 50
+            extras["policy_value"] = {"value": 1024 / (pms * 1e-3), "unit": "observations/s", "ms_per_batch": pms, "dtype": "bf16",
+                                      "config": {"workload": "TransformerAlphaGoZeroModel inference, config/default.yml dims (d=640, 8 layers, 98 tokens), "
+                                                             "random-init weights, synthetic observations, batch 1024, CUDA graph"},
+                                      "e2e": {"value": 1024 / pe2e, "unit": "observations/s", "h2d_bytes_per_step": int(obs.nbytes),
+                                              "d2h_bytes_per_step": int(probs.nbytes + val.nbytes)},
+                                      "predict_latency_us": p1lat * 1e6}
+            del pred, net, dobs
         barrier()
 
     clocks = sampler.stop() if rank == 0 else None   # sampled through the timed steps and the Monte-Carlo section
