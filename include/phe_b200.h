@@ -186,6 +186,31 @@ int phe_nn_embed_obs(const int32_t *obs, const int32_t *field_start, const void 
                      const void *starters, void *out, int64_t batch, int n_fields, int n_starters, int de, int dp,
                      int n_rows, int dtype, void *stream);
 
+/* ---- observation encoder (Env.get_obs, env/env.py:416-581) -------------------------------------------------- */
+#define PHE_OBS_CUTTERS      16   /* cutter instances of env/env.py:52-81, in the order listed below */
+#define PHE_OBS_MAX_THR      20   /* longest threshold list (CUTTER_SELF_DEFAULT_LIST has 19) */
+#define PHE_OBS_CARD_NONE    52   /* card slot not dealt yet   -> (figure 14, decor 5), env/env.py:709 */
+#define PHE_OBS_CARD_HIDDEN  53   /* dealt but not observable  -> (figure 13, decor 4), env/env.py:717-719 */
+/* n observations -> obs_out int32[n][F], F = phe_obs_num_fields(n_bins, n_other, n_hist) (93 for the reference's
+ * heads-up configuration: n_bins 10, n_other 1, n_hist 24), field order of Env._map_obs_idx_to_model_index
+ * (env/env.py:383-408).  All inputs are device pointers:
+ *   round_role int32[n][2]   current round, acting player's position relative to the button (env/env.py:441-443)
+ *   cards      uint8[n][7]   hand 2, flop 3, turn, river as ids, or PHE_OBS_CARD_NONE / PHE_OBS_CARD_HIDDEN
+ *   values     int64[n][5]   game_init_value, pot_value, acting player's init / left / history-bet value
+ *   bins       int64[n][n_bins]  infoset.bin_bet_value_list (-1 = bin not available)
+ *   others     int64[n][n_other][3]  status, value left, init value of the other players by relative position
+ *   history    uint8[n][n_hist]  acting player's, then the opponent's action bins, padded with num_action_bins
+ *   cut_table  { double thr[16][20]; int32 len[16]; }: threshold lists of the cutters, in this order:
+ *              0 init/game_init, 1 left/game_init, 2 left/init, 3 bet/pot, 4-6 bet/{game_init, init, left},
+ *              7-9 pot/{game_init, init, left}, 10 action/pot, 11-13 action/{game_init, init, left} (10-13 have the
+ *              extra invalid bin), 14 other left/init, 15 other init/acting init.
+ * A ratio is an IEEE double division of the two integers, compared as tools/biner.py:8-27 does. */
+int phe_obs_num_fields(int n_bins, int n_other, int n_hist);
+uint64_t phe_obs_cut_table_bytes(void);
+int phe_encode_obs(const int32_t *round_role, const uint8_t *cards, const int64_t *values, const int64_t *bins,
+                   const int64_t *others, const uint8_t *history, const void *cut_table, int64_t n, int n_bins,
+                   int n_other, int n_hist, int32_t *obs_out, void *stream);
+
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
 uint64_t phe_launch_count(void);
 

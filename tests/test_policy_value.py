@@ -85,7 +85,11 @@ def test_bad_observations_are_rejected(golden):
     obs = np.asarray(case["obs"][:2], dtype=np.int32)
     m.check_observations(obs)
     bad = obs.copy()
-    bad[1, 0] = 4                                   # round field has 4 values
+    bad[1, -1] = 13                                 # last field: 13 rows, index 13 leaves the table
+    with pytest.raises(ValueError):
+        m.check_observations(bad)
+    bad = obs.copy()
+    bad[0, 3] = -1
     with pytest.raises(ValueError):
         m.check_observations(bad)
     with pytest.raises(ValueError):

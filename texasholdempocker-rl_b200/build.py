@@ -42,7 +42,7 @@ def nvcc_path():
 def build_library(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     if force or _stale(LIB, _all_deps()):
-        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + _sources(["phe_kernels.cu", "phe_nn.cu", "phe_tables.cpp"])
+        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + _sources(["phe_kernels.cu", "phe_nn.cu", "phe_obs.cu", "phe_tables.cpp"])
         subprocess.check_call(cmd)
     return LIB
 

@@ -251,14 +251,21 @@ class PolicyValueNet(nn.Module):
         return (torch.softmax(self.action_prob_dense(h[:, 0]).float(), dim=1), self.reward_value_dense(h[:, 1]).squeeze(1).float())
 
     def check_observations(self, x):
-        """ValueError if a field is outside its vocabulary (the reference would read a neighbouring field's embedding rows)."""
+        """ValueError if an observation would index outside the embedding table.
+
+        Quirk kept from the reference: a cutter with n thresholds emits n + 1 bins (n + 2 with the invalid bin,
+        tools/biner.py:2-5) but rl/models.py:39-67 allots the field only n (n + 1) rows, so the top bin of every ratio
+        feature reads the first row of the NEXT field's range.  Env.get_obs produces such values routinely
+        (tests/golden/obs_run.json.gz), so they are accepted here as they are by the reference; only indices that
+        leave the table are rejected."""
         x = torch.as_tensor(x)
         if x.dim() != 2 or x.shape[1] != self.n_fields:
             raise ValueError(f"observations must be [B, {self.n_fields}], got {tuple(x.shape)}")
-        bad = (x < 0) | (x >= self._field_sizes.to(x.device))
+        idx = x.to(torch.int64) + self.env_embedding.field_start_idx_array.to(x.device, torch.int64)
+        bad = (x < 0) | (idx >= self.env_embedding.field_embedding.num_embeddings)
         if bool(bad.any()):
             b, f = [int(v) for v in bad.nonzero()[0]]
-            raise ValueError(f"observation {b}: field {f} = {int(x[b, f])} outside [0, {int(self._field_sizes[f])})")
+            raise ValueError(f"observation {b}: field {f} = {int(x[b, f])} indexes outside the embedding table")
 
 
 # ---- the predictor -------------------------------------------------------------------------------------------------
