@@ -14,7 +14,7 @@ from . import _native
 from .cardset import DECK, Card, CardDecor, CardFigure, card_id, card_to_evaluator, cards_to_mask, ids_to_masks, mask_to_ids
 from .equity import deal, determinise, equity_mc, equity_plan, pack_states, plan_num_deals, random_states, showdown, win_probability
 from .evaluator import enumerate_c52_7, eval7, evaluate_cards
-from . import observation, policy_value
+from . import observation, policy_value, records
 from .observation import ObsEncoder
 from .policy_value import BatchedPredictor, PolicyValueNet
 from .service import simulate_processes, solve_tasks, winning_probability
