@@ -216,7 +216,7 @@ constexpr uint32_t DEAL_PAIR_LIMIT = 49u * 1326u;    // 64,974
 constexpr uint32_t DEAL_SINGLE_LIMIT = 1260u * 52u;  // 65,520
 
 // r % 1326 and r % 52 for r < 65536 by multiply-shift (exact for every 16-bit r; checked exhaustively in the tests)
-PHE_HD uint32_t mod1326_u16(uint32_t r) { return r - (((r >> 1) * 50611u) >> 25) * 1326u; }   // 1326 = 2 * 663
+PHE_HD uint32_t mod1326_u16(uint32_t r) { return r - umulhi32(r, 3239054u) * 1326u; }   // floor(r / 1326) = (r * 3239054) >> 32 for r < 2^16: two FMA-pipe instructions
 PHE_HD uint32_t mod52_u16(uint32_t r) { return r - ((r * 40330u) >> 21) * 52u; }
 
 struct GlobalDealTab {          // host / small kernels

@@ -480,7 +480,7 @@ template <class Tab, class DealTab>
 __device__ __forceinline__ void equity_mc_body(const Tab& tab, const DealTab& dt, const ulonglong2* __restrict__ states, int64_t n_states,
                                                int n_opp_default, uint64_t rollouts, uint64_t sample_offset, uint64_t seed,
                                                uint32_t state_base, unsigned long long* __restrict__ wtl, uint32_t chunk,
-                                               SmemSlots slots)
+                                               SmemSlots slots, unsigned int* __restrict__ item_counter)
 {
     const HashParams hp = c_hp;
     const uint32_t lane = threadIdx.x & 31;
@@ -488,7 +488,17 @@ __device__ __forceinline__ void equity_mc_body(const Tab& tab, const DealTab& dt
     const uint64_t nwarps = (uint64_t)gridDim.x * warps_per_cta;
     const uint64_t chunks_per_state = (rollouts + chunk - 1) / chunk;
     const uint64_t items = (uint64_t)n_states * chunks_per_state;
-    for (uint64_t item = (uint64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); item < items; item += nwarps) {
+    // Items cost differently (a pre-flop six-max deal places 15 cards, a river deal 10) and SMs do not run at one speed:
+    // with a counter the warps pull items as they finish (the static round-robin left SMs idle for up to 15 % of the
+    // kernel).  Counts are integer sums, so the schedule does not change the result.
+    uint64_t item = (uint64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+    for (;; item += nwarps) {
+        if (item_counter) {
+            uint32_t nxt = 0;
+            if (lane == 0) nxt = atomicAdd(item_counter, 1u);
+            item = __shfl_sync(0xFFFFFFFFu, nxt, 0);
+        }
+        if (item >= items) break;
         const uint64_t s = item / chunks_per_state, ch = item - s * chunks_per_state;
         const ulonglong2 st = states[s];
         const uint64_t known = st.x & CARD_BITS, hero = st.y & CARD_BITS;
@@ -517,7 +527,7 @@ __device__ __forceinline__ void equity_mc_body(const Tab& tab, const DealTab& dt
 __global__ void __launch_bounds__(kCtaThreads, 1)
 k_equity_mc_smem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict__ g_dealtab, const ulonglong2* __restrict__ states,
                  int64_t n_states, int n_opp, uint64_t rollouts, uint64_t sample_offset, uint64_t seed, uint32_t state_base,
-                 unsigned long long* __restrict__ wtl, uint32_t chunk)
+                 unsigned long long* __restrict__ wtl, uint32_t chunk, unsigned int* __restrict__ counters)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* s_deal = reinterpret_cast<uint64_t*>(smem + kSmemTabOnly);
@@ -528,7 +538,16 @@ k_equity_mc_smem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
     const SharedTab tab{sb};
     const SharedDealTab dt{sb + kSmemTabOnly};
     const SmemSlots slots{sb + kSmemTabOnly + kDealTabBytes + 4u * threadIdx.x, 4u * blockDim.x, 0ull};
-    equity_mc_body(tab, dt, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk, slots);
+    equity_mc_body(tab, dt, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk, slots, counters);
+    // completion ticket: the last CTA re-arms the {item counter, ticket} pair for the next launch that draws it
+    __shared__ uint32_t s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(counters + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        counters[0] = 0;
+        counters[1] = 0;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -540,7 +559,7 @@ k_equity_mc_gmem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
     const GlobalTab tab{g_tab};
     const GlobalDealTab dt{g_dealtab};
     const SmemSlots slots{(uint32_t)__cvta_generic_to_shared(s_slots) + 4u * threadIdx.x, 4u * blockDim.x, 0ull};
-    equity_mc_body(tab, dt, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk, slots);
+    equity_mc_body(tab, dt, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk, slots, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1145,6 +1164,7 @@ int phe_equity_mc(const uint64_t* states, int64_t n_states, int n_opp, uint64_t 
     if (chunk < 32) chunk = 32;
     if (chunk > 8192) chunk = 8192;
     if (chunk > ((rollouts + 31) & ~(uint64_t)31)) chunk = (rollouts + 31) & ~(uint64_t)31;
+    while ((uint64_t)n_states * ((rollouts + chunk - 1) / chunk) > (1ull << 31) && chunk < (1ull << 31)) chunk *= 2;   // 32-bit item counter
     const uint64_t items = (uint64_t)n_states * ((rollouts + chunk - 1) / chunk);
     const auto* sp = reinterpret_cast<const ulonglong2*>(states);
     auto* wp = reinterpret_cast<unsigned long long*>(wtl);
@@ -1155,7 +1175,8 @@ int phe_equity_mc(const uint64_t* states, int64_t n_states, int n_opp, uint64_t 
     } else {
         uint64_t ctas = (items + 31) / 32;
         if (ctas > (uint64_t)cx->sm_count) ctas = cx->sm_count;
-        k_equity_mc_smem<<<(unsigned)ctas, kCtaThreads, kSmemMc, st>>>(cx->d_image, cx->d_pairmask, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk);
+        unsigned int* counters = cx->d_counters + 2 * (cx->next_counter.fetch_add(1, std::memory_order_relaxed) % kCounterRing);
+        k_equity_mc_smem<<<(unsigned)ctas, kCtaThreads, kSmemMc, st>>>(cx->d_image, cx->d_pairmask, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk, counters);
     }
     return after_launch("equity_mc launch");
 }
