@@ -63,6 +63,10 @@ def test_eval7_unaligned_views(phe, oracle, torch):
     want = oracle.rank7_batch(ids)
     got = phe.eval7(masks[1:])                        # 8-byte but not 16-byte aligned input
     assert (got.cpu().numpy().astype(np.uint16) == want[1:]).all()
+    dids = torch.from_numpy(ids).cuda()
+    for off in (1, 2, 3, 4):                          # id rows start 7 bytes apart: only every fourth view is word aligned
+        got = phe.eval7(dids[off:])
+        assert (got.cpu().numpy().astype(np.uint16) == want[off:]).all()
 
 
 def test_eval7_every_rank_multiset(phe, oracle, torch):

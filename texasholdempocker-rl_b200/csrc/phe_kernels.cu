@@ -40,6 +40,7 @@ static constexpr uint32_t kEnumBinOff = kEnumBarOff + 16;                      /
 static constexpr uint32_t kSmemEnum = kEnumBinOff + 8 * 64 * 4;
 static constexpr uint32_t kSmemTabOnly = kSmemTab + 16;
 static constexpr uint32_t kSmemPairs = kSmemTabOnly + N_PAIRS * 8;
+static constexpr uint32_t kSmemEvalIds = kSmemTabOnly + (kCtaThreads / 32) * 896;      // + per-warp transpose strips of the id layout
 static constexpr uint32_t kDealTabBytes = DEALTAB_ENTRIES * 8;                 // 11,024
 static constexpr uint32_t kSmemMc = kSmemTabOnly + kDealTabBytes + MAX_PAIR_SLOTS * 4 * kCtaThreads;   // + deal table + slot scratch
 
@@ -166,7 +167,66 @@ k_eval7_smem(const uint16_t* __restrict__ g_tab, const void* __restrict__ hands,
     } else {
         grid_launch_dependents();
         const uint8_t* h = static_cast<const uint8_t*>(hands);
-        for (int64_t i = gtid; i < n; i += nthr) out[i] = (uint16_t)eval7(hand_from_ids(h + 7 * i), tab, hp);
+        // id layout: a warp takes 128 consecutive hands = 896 bytes = 224 words.  The words are loaded coalesced (7 per
+        // lane), transposed through a per-warp shared-memory strip (lane L then owns words 7L..7L+6 = its four hands;
+        // stride 7 is conflict free), and the 28 ids become four card sets with packed byte arithmetic:
+        // pos = 16*(id&3) + (id>>2) for four ids per word at once, bit = 1 << pos by two clamping 32-bit shifts
+        // (pos for the low word, pos ^ 32 for the high word: the half that does not hold the bit shifts out to 0).
+        const bool vec = ((reinterpret_cast<uintptr_t>(h) & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+        const int64_t nchunk = vec ? (n >> 7) : 0;
+        const uint32_t* hw = reinterpret_cast<const uint32_t*>(h);
+        const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+        uint32_t* stg = reinterpret_cast<uint32_t*>(smem + kSmemTabOnly) + wic * 224u;
+        const int64_t nwarps = nthr >> 5;
+        int64_t c = gtid >> 5;
+        uint32_t ld[7];
+        if (c < nchunk) {
+#pragma unroll
+            for (int j = 0; j < 7; j++) ld[j] = __ldcs(hw + c * 224 + lane + 32 * j);
+        }
+        for (; c < nchunk; c += nwarps) {
+#pragma unroll
+            for (int j = 0; j < 7; j++) stg[lane + 32 * j] = ld[j];
+            __syncwarp();
+            uint32_t w[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) w[j] = stg[7 * lane + j];
+            __syncwarp();
+            const int64_t cn = c + nwarps;
+            if (cn < nchunk) {
+#pragma unroll
+                for (int j = 0; j < 7; j++) ld[j] = __ldcs(hw + cn * 224 + lane + 32 * j);
+            }
+            uint32_t plo[7], phi[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                plo[j] = ((w[j] << 4) & 0x30303030u) | ((w[j] >> 2) & 0x0F0F0F0Fu);
+                phi[j] = plo[j] ^ 0x20202020u;
+            }
+            uint32_t r[4];
+#pragma unroll
+            for (int hnd = 0; hnd < 4; hnd++) {
+                uint32_t lo = 0, hi = 0;
+#pragma unroll
+                for (int k = 0; k < 7; k++) {
+                    const int bi = 7 * hnd + k;
+                    const uint32_t sel = 0x4440u | (uint32_t)(bi & 3);              // byte (bi & 3) of the word, zero extended
+                    uint32_t sl, sh, bl, bh;
+                    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(sl) : "r"(plo[bi >> 2]), "r"(sel));
+                    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(sh) : "r"(phi[bi >> 2]), "r"(sel));
+                    asm("shl.b32 %0, 1, %1;" : "=r"(bl) : "r"(sl));                  // clamps: shift >= 32 gives 0
+                    asm("shl.b32 %0, 1, %1;" : "=r"(bh) : "r"(sh));
+                    lo |= bl;
+                    hi |= bh;
+                }
+                r[hnd] = eval7(((uint64_t)hi << 32) | lo, tab, hp);
+            }
+            uint2 o;
+            o.x = r[0] | (r[1] << 16);
+            o.y = r[2] | (r[3] << 16);
+            __stcs(reinterpret_cast<uint2*>(out) + (c * 32 + lane), o);
+        }
+        for (int64_t i = nchunk * 128 + gtid; i < n; i += nthr) out[i] = (uint16_t)eval7(hand_from_ids(h + 7 * i), tab, hp);
     }
 }
 
@@ -894,7 +954,7 @@ void init_device(int device)
     chk(cudaFuncSetAttribute(k_equity_plan_pairs_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPairs), "attr equity_plan_pairs");
     chk(cudaMemcpyToSymbol(c_hp, &g_hp, sizeof g_hp), "cudaMemcpyToSymbol(c_hp)");
     chk(cudaMemcpyToSymbol(c_binom, g_binom, sizeof g_binom), "cudaMemcpyToSymbol(c_binom)");
-    chk(cudaFuncSetAttribute(k_eval7_smem<PHE_LAYOUT_IDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr eval7 ids");
+    chk(cudaFuncSetAttribute(k_eval7_smem<PHE_LAYOUT_IDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEvalIds), "attr eval7 ids");
     chk(cudaFuncSetAttribute(k_eval7_smem<PHE_LAYOUT_MASKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr eval7 masks");
     chk(cudaFuncSetAttribute(k_enum7, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEnum), "attr enum7");
     chk(cudaFuncSetAttribute(k_equity_mc_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMc), "attr equity_mc");
@@ -1016,7 +1076,7 @@ int phe_eval7(const void* hands, int layout, int64_t n, uint16_t* out, void* str
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)cx->sm_count);
         cfg.blockDim = dim3(kCtaThreads);
-        cfg.dynamicSmemBytes = kSmemTabOnly;
+        cfg.dynamicSmemBytes = layout == PHE_LAYOUT_IDS ? kSmemEvalIds : kSmemTabOnly;
         cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
