@@ -211,6 +211,15 @@ int phe_encode_obs(const int32_t *round_role, const uint8_t *cards, const int64_
                    const int64_t *others, const uint8_t *history, const void *cut_table, int64_t n, int n_bins,
                    int n_other, int n_hist, int32_t *obs_out, void *stream);
 
+/* softmax(Q K^T / sqrt(head_dim)) V per (batch, head) for sequences of at most 112 tokens (the model has 98), bf16:
+ * the self-attention of nn.TransformerEncoderLayer (rl/models.py:446-447).  q [batch][s_q][heads*head_dim] and
+ * k, v [batch][s_kv][heads*head_dim] are addressed with element strides (batch stride, row stride), so the packed
+ * output of the fused in-projection can be used in place; out is contiguous [batch][s_q][heads*head_dim].
+ * head_dim 16 or 64; pointers and strides multiples of 16 bytes. */
+int phe_nn_attention(const void *q, const void *k, const void *v, void *out, int64_t batch, int heads, int s_q,
+                     int s_kv, int head_dim, int64_t q_batch_stride, int64_t q_row_stride, int64_t kv_batch_stride,
+                     int64_t kv_row_stride, int dtype, void *stream);
+
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
 uint64_t phe_launch_count(void);
 

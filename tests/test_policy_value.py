@@ -194,3 +194,26 @@ def test_embed_obs_kernel_gpu(golden, dtype):
         with torch.no_grad():
             ref = cpu.embed(obs)
         np.testing.assert_allclose(got.float().cpu().numpy(), ref.numpy(), atol=1e-6 if dtype == torch.float32 else 3e-2, rtol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,D", [(10, 64), (6, 16)])
+@pytest.mark.parametrize("Sq,S", [(98, 98), (2, 98), (5, 98), (1, 1), (17, 33), (112, 112), (16, 97)])
+def test_attention_kernel_gpu(H, D, Sq, S):
+    """phe_nn_attention against a plain fp32 PyTorch softmax(q k^T / sqrt(D)) v of the same bf16 inputs, on views into
+    packed projections (the strides the model uses).  Tolerance: probabilities and outputs are rounded to bf16
+    (2^-8 relative) -> 2e-2 absolute on O(1) outputs."""
+    B = 7
+    g = torch.Generator(device="cpu").manual_seed(H * 1000 + Sq * 10 + S)
+    qkv = torch.randn(B, S, 3, H, D, generator=g).to(torch.bfloat16).cuda()
+    qsrc = torch.randn(B, Sq, H, D, generator=g).to(torch.bfloat16).cuda()
+    k, v = qkv[:, :, 1], qkv[:, :, 2]
+    q = qkv[:, :, 0] if Sq == S else qsrc
+    before = phe._native.launch_count()
+    got = pv._attention(q, k, v)
+    assert phe._native.launch_count() == before + 1
+    qf, kf, vf = q.float().transpose(1, 2), k.float().transpose(1, 2), v.float().transpose(1, 2)
+    want = torch.softmax(qf @ kf.transpose(-1, -2) / D ** 0.5, dim=-1) @ vf
+    want = want.transpose(1, 2).reshape(B, Sq, H * D)
+    assert got.shape == want.shape and got.dtype == torch.bfloat16
+    np.testing.assert_allclose(got.float().cpu().numpy(), want.cpu().numpy(), atol=2e-2, rtol=0)

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <mutex>
 
 #include "../../include/phe_b200.h"
 
@@ -225,3 +226,242 @@ int phe_nn_embed_obs(const int32_t* obs, const int32_t* field_start, const void*
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// phe_nn_attention: softmax(Q K^T / sqrt(D)) V for the short sequences of this model (98 tokens, <= 112), bf16.
+// One CTA of four warps per (batch, head): K, V and Q of that head are staged once in shared memory (<= 48 KB), each
+// warp takes 16-row query tiles, keeps the whole 16 x 112 score tile in registers (no online-softmax rescaling is
+// needed at this length), and feeds the probabilities straight back as the A operand of the P V product
+// (mma.sync.m16n8k16, ldmatrix / ldmatrix.trans operands).  The generic flash kernels of cuDNN / FA2 run this shape at
+// 2.6x its memory floor; here the traffic is the algorithmic one: Q, K, V read once, O written once
+// ((2 S_q + 2 S_kv) * D * 2 bytes per head).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kAttnMaxKeys = 112;       // 7 k-steps of 16 keys
+constexpr int kAttnWarps = 8;          // 98 query rows = 7 tiles of 16: one round, 7 of the 8 warps busy in the MMA phase
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x2(uint32_t (&r)[2], uint32_t addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], uint32_t addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ float ex2(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
+{
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// D = head dimension (16 or 64).  Rows of the shared tiles are padded by 8 elements (16 bytes): the 8 row addresses
+// of an ldmatrix then fall into distinct bank groups.  Persistent CTAs (two per SM) walk the (batch, head) pairs with a
+// two-stage shared-memory pipeline: the cp.async copies of the next pair are in flight while the current one is in the
+// MMA phase -- with one-shot CTAs the load and MMA phases of the four resident CTAs alternated and the kernel ran at
+// half of the memory rate.
+template <int D>
+struct AttnSmem {
+    static constexpr int LD = D + 8;
+    static constexpr int kTile = kAttnMaxKeys * LD;            // elements of one K / V / Q tile
+    static constexpr uint32_t kBytes = 2u * 3u * kTile * 2u;   // two stages of {K, V, Q}
+};
+
+template <int D>
+__global__ void __launch_bounds__(kAttnWarps * 32, 2)
+k_attention(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+            __nv_bfloat16* __restrict__ out, int total_bh, int heads, int s_q, int s_kv, int64_t q_bs, int64_t q_rs, int64_t kv_bs,
+            int64_t kv_rs, float scale_log2e)
+{
+    constexpr int LD = AttnSmem<D>::LD;
+    constexpr int kTile = AttnSmem<D>::kTile;
+    constexpr int VPR = D / 8;                 // 16-byte vectors per row
+    extern __shared__ __align__(16) unsigned char attn_smem[];
+    __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(attn_smem);          // stage st: K at (3 st) kTile, V at (3 st + 1) kTile, Q at (3 st + 2) kTile
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q_tiles = (s_q + 15) >> 4;
+    const int q_rows = q_tiles * 16;
+    // rows beyond the sequence stay zero for the whole launch (the copies below never touch them)
+    for (int i = tid; i < 2 * kAttnMaxKeys * VPR; i += blockDim.x) {
+        const int st = i / (kAttnMaxKeys * VPR), j = i - st * (kAttnMaxKeys * VPR);
+        const int r = j / VPR, c = j - r * VPR;
+        __nv_bfloat16* base = sm + 3 * st * kTile + r * LD + c * 8;
+        if (r >= s_kv) {
+            *reinterpret_cast<uint4*>(base) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(base + kTile) = make_uint4(0, 0, 0, 0);
+        }
+        if (r >= s_q) *reinterpret_cast<uint4*>(base + 2 * kTile) = make_uint4(0, 0, 0, 0);
+    }
+    auto issue = [&](int bh, int st) {
+        const int b = bh / heads, h = bh - b * heads;
+        const __nv_bfloat16* kb = k + (int64_t)b * kv_bs + (int64_t)h * D;
+        const __nv_bfloat16* vb = v + (int64_t)b * kv_bs + (int64_t)h * D;
+        const __nv_bfloat16* qb = q + (int64_t)b * q_bs + (int64_t)h * D;
+        __nv_bfloat16* sk = sm + 3 * st * kTile;
+        for (int i = tid; i < s_kv * VPR; i += blockDim.x) {
+            const int r = i / VPR, c = i - r * VPR;
+            cp_async16(sk + r * LD + c * 8, reinterpret_cast<const uint4*>(kb + (int64_t)r * kv_rs) + c);
+            cp_async16(sk + kTile + r * LD + c * 8, reinterpret_cast<const uint4*>(vb + (int64_t)r * kv_rs) + c);
+        }
+        for (int i = tid; i < s_q * VPR; i += blockDim.x) {
+            const int r = i / VPR, c = i - r * VPR;
+            cp_async16(sk + 2 * kTile + r * LD + c * 8, reinterpret_cast<const uint4*>(qb + (int64_t)r * q_rs) + c);
+        }
+    };
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int NT = kAttnMaxKeys / 8;       // 14 key tiles of 8
+    constexpr int KS = D / 16;                 // k-steps of Q K^T
+    constexpr int DT = D / 8;
+    const int nt_live = (s_kv + 7) >> 3;       // key tiles that hold at least one real key
+    int bh = blockIdx.x;
+    if (bh < total_bh) issue(bh, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int it = 0; bh < total_bh; bh += gridDim.x, it++) {
+        const int st = it & 1;
+        if (bh + (int)gridDim.x < total_bh) issue(bh + gridDim.x, st ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        const uint32_t a_k = (uint32_t)__cvta_generic_to_shared(sm + 3 * st * kTile), a_v = a_k + 2u * kTile, a_q = a_k + 4u * kTile;
+        const int b = bh / heads, h = bh - b * heads;
+        for (int qt = warp; qt < q_tiles; qt += kAttnWarps) {
+            // ---- S = Q K^T ----
+            uint32_t aq[KS][4];
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++)
+                ldmatrix_x4(aq[ks], a_q + 2u * (uint32_t)((qt * 16 + (lane & 15)) * LD + ks * 16 + (lane >> 4) * 8));
+            float s[NT][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+            // k-step outermost: consecutive HMMAs write different accumulators (14 independent chains instead of 4-deep
+            // dependent ones; the kernel was stalled on HMMA latency with only four warps per scheduler)
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) {
+#pragma unroll
+                for (int nt = 0; nt < NT; nt += 2) {
+                    if (nt < nt_live) {
+                        // one ldmatrix.x4 = the B fragments of two key tiles: (keys nt*8.., dims lo / hi), (keys (nt+1)*8.., dims lo / hi)
+                        uint32_t bk[4];
+                        ldmatrix_x4(bk, a_k + 2u * (uint32_t)((nt * 8 + (lane & 7) + ((lane >> 4) & 1) * 8) * LD + ks * 16 + ((lane >> 3) & 1) * 8));
+                        const uint32_t b0[2] = {bk[0], bk[1]}, b1[2] = {bk[2], bk[3]};
+                        mma_bf16(s[nt], aq[ks], b0);
+                        mma_bf16(s[nt + 1], aq[ks], b1);
+                    }
+                }
+            }
+            // ---- softmax over the keys (rows g and g + 8 of the tile; a row lives in the four lanes of a quad) ----
+            // No masking: padded keys have K = 0, hence score 0 and probability exp2(-max * scale), and V = 0, so they
+            // add nothing to P V; their (112 - s_kv) equal terms are taken out of the row sum in closed form.  The
+            // running maximum therefore includes 0, which any valid softmax shift may.
+            float m0 = 0.f, m1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) {
+                m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+                m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+            }
+            m0 = fmaxf(m0, __shfl_xor_sync(0xFFFFFFFFu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xFFFFFFFFu, m0, 2));
+            m1 = fmaxf(m1, __shfl_xor_sync(0xFFFFFFFFu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xFFFFFFFFu, m1, 2));
+            const float c0 = m0 * scale_log2e, c1 = m1 * scale_log2e;       // exp2(s * scale - max * scale): one FFMA + one MUFU per score
+            float l0 = 0.f, l1 = 0.f;
+            uint32_t p[NT][2];                       // probabilities as bf16 pairs: [nt][0] row g, [nt][1] row g + 8
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) {
+                const float e0 = ex2(fmaf(s[nt][0], scale_log2e, -c0)), e1 = ex2(fmaf(s[nt][1], scale_log2e, -c0));
+                const float e2 = ex2(fmaf(s[nt][2], scale_log2e, -c1)), e3 = ex2(fmaf(s[nt][3], scale_log2e, -c1));
+                l0 += e0 + e1;
+                l1 += e2 + e3;
+                p[nt][0] = pack_bf16(e0, e1);
+                p[nt][1] = pack_bf16(e2, e3);
+            }
+            l0 += __shfl_xor_sync(0xFFFFFFFFu, l0, 1); l0 += __shfl_xor_sync(0xFFFFFFFFu, l0, 2);
+            l1 += __shfl_xor_sync(0xFFFFFFFFu, l1, 1); l1 += __shfl_xor_sync(0xFFFFFFFFu, l1, 2);
+            const float npad = (float)(kAttnMaxKeys - s_kv);
+            const float inv0 = 1.f / (l0 - npad * ex2(-c0)), inv1 = 1.f / (l1 - npad * ex2(-c1));
+            // ---- O = P V: the score accumulators of key tiles (2j, 2j + 1) are exactly the A fragment of k-step j ----
+            float o[DT][4];
+#pragma unroll
+            for (int dt = 0; dt < DT; dt++) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+            for (int j = 0; j < NT / 2; j++) {
+                if (2 * j < nt_live) {
+                    const uint32_t ap[4] = {p[2 * j][0], p[2 * j][1], p[2 * j + 1][0], p[2 * j + 1][1]};
+#pragma unroll
+                    for (int dt = 0; dt < DT; dt += 2) {
+                        // transposed x4: (keys lo / hi, dims dt*8..) and (keys lo / hi, dims (dt+1)*8..)
+                        uint32_t bv[4];
+                        ldmatrix_x4_trans(bv, a_v + 2u * (uint32_t)((j * 16 + (lane & 15)) * LD + dt * 8 + ((lane >> 4) & 1) * 8));
+                        const uint32_t b0[2] = {bv[0], bv[1]}, b1[2] = {bv[2], bv[3]};
+                        mma_bf16(o[dt], ap, b0);
+                        mma_bf16(o[dt + 1], ap, b1);
+                    }
+                }
+            }
+            const int r0 = qt * 16 + g, r1 = r0 + 8;
+            __nv_bfloat16* ob = out + ((int64_t)b * s_q) * heads * D + (int64_t)h * D;
+#pragma unroll
+            for (int dt = 0; dt < DT; dt++) {
+                if (r0 < s_q) *reinterpret_cast<uint32_t*>(ob + (int64_t)r0 * heads * D + dt * 8 + 2 * t) = pack_bf16(o[dt][0] * inv0, o[dt][1] * inv0);
+                if (r1 < s_q) *reinterpret_cast<uint32_t*>(ob + (int64_t)r1 * heads * D + dt * 8 + 2 * t) = pack_bf16(o[dt][2] * inv1, o[dt][3] * inv1);
+            }
+        }
+        __syncthreads();           // every warp is done with this stage before the next iteration's copies overwrite it
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+}  // namespace
+
+extern "C" int phe_nn_attention(const void* q, const void* k, const void* v, void* out, int64_t batch, int heads, int s_q, int s_kv,
+                                int head_dim, int64_t q_batch_stride, int64_t q_row_stride, int64_t kv_batch_stride, int64_t kv_row_stride,
+                                int dtype, void* stream)
+{
+    if (batch < 0 || heads <= 0 || s_q <= 0 || s_kv <= 0 || s_q > kAttnMaxKeys || s_kv > kAttnMaxKeys || dtype != PHE_DTYPE_BF16) return PHE_EINVAL;
+    if (head_dim != 16 && head_dim != 64) return PHE_EINVAL;
+    if (batch == 0) return PHE_OK;
+    if (!q || !k || !v || !out) return PHE_EINVAL;
+    if (batch * heads > 0x7FFFFFFFll) return PHE_EINVAL;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out);
+    if ((al & 15) || ((q_batch_stride | q_row_stride | kv_batch_stride | kv_row_stride) & 7)) return PHE_EINVAL;      // 16-byte rows
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float scale_log2e = 1.4426950408889634f / sqrtf((float)head_dim);
+    const int total = (int)(batch * heads);
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned blocks = (unsigned)(total < 2 * sms ? total : 2 * sms);
+    static std::once_flag attr_once[16];
+    std::call_once(attr_once[dev & 15], [] {
+        cudaFuncSetAttribute(k_attention<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<64>::kBytes);
+        cudaFuncSetAttribute(k_attention<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<16>::kBytes);
+    });
+    const auto *qp = static_cast<const __nv_bfloat16*>(q), *kp = static_cast<const __nv_bfloat16*>(k), *vp = static_cast<const __nv_bfloat16*>(v);
+    auto* op = static_cast<__nv_bfloat16*>(out);
+    if (head_dim == 64)
+        k_attention<64><<<blocks, kAttnWarps * 32, AttnSmem<64>::kBytes, st>>>(qp, kp, vp, op, total, heads, s_q, s_kv, q_batch_stride, q_row_stride, kv_batch_stride, kv_row_stride, scale_log2e);
+    else
+        k_attention<16><<<blocks, kAttnWarps * 32, AttnSmem<16>::kBytes, st>>>(qp, kp, vp, op, total, heads, s_q, s_kv, q_batch_stride, q_row_stride, kv_batch_stride, kv_row_stride, scale_log2e);
+    return nn_after_launch();
+}

@@ -119,6 +119,24 @@ def _add_layernorm(x, residual, norm):
     return F.layer_norm(x + residual, (d,), norm.weight, norm.bias, norm.eps)
 
 
+def _attention(q, k, v):
+    """softmax(q k^T / sqrt(D)) v for q [B, Sq, H, D], k / v [B, S, H, D] (views into the packed projections) -> [B, Sq, H*D].
+    bf16 on the device with S <= 112 and D in (16, 64): phe_nn_attention (one CTA per (batch, head), csrc/phe_nn.cu);
+    otherwise PyTorch's scaled_dot_product_attention."""
+    B, Sq, H, D = q.shape
+    S = k.shape[1]
+    if (q.is_cuda and q.dtype == torch.bfloat16 and D in (16, 64) and S <= 112 and Sq <= 112 and k.stride() == v.stride()
+            and q.stride(3) == 1 and k.stride(3) == 1 and q.stride(2) == D and k.stride(2) == D
+            and all(st % 8 == 0 for st in (q.stride(0), q.stride(1), k.stride(0), k.stride(1)))
+            and all(t.data_ptr() % 16 == 0 for t in (q, k, v))):
+        out = torch.empty((B, Sq, H * D), dtype=q.dtype, device=q.device)
+        N.check(N.lib().phe_nn_attention(_ptr(q), _ptr(k), _ptr(v), _ptr(out), B, H, Sq, S, D, q.stride(0), q.stride(1), k.stride(0), k.stride(1),
+                                         _DTYPES[q.dtype], _stream()))
+        return out
+    a = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2))
+    return a.transpose(1, 2).reshape(B, Sq, H * D)
+
+
 def _linear_relu(x, lin):
     """relu(x @ W^T + b) with bias and ReLU in the GEMM epilogue (cuBLASLt) on the device; plain ops on the host."""
     if x.is_cuda:
@@ -151,8 +169,7 @@ class _EncoderLayer(nn.Module):
             q = F.linear(xq, sa.in_proj_weight[:d], sa.in_proj_bias[:d]).view(B, n_query, H, d // H)
             kv = F.linear(x, sa.in_proj_weight[d:], sa.in_proj_bias[d:]).view(B, S, 2, H, d // H)
             k, v = kv[:, :, 0], kv[:, :, 1]
-        a = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2))
-        a = a.transpose(1, 2).reshape(B, xq.shape[1], d)
+        a = _attention(q, k, v)
         y = _add_layernorm(sa.out_proj(a), xq, self.norm1)
         return _add_layernorm(self.linear2(_linear_relu(y, self.linear1)), y, self.norm2)
 
