@@ -285,7 +285,8 @@ def main():
                                "roofline_frac_nominal": mc_val * w_roll / (NOMINAL_INT_PEAK * world),
                                "checksum": int(wtl[:, 0].sum().item())}
         # --- materialised-hands micro-config: 2^25 card sets (268 MB > L2) -> ranks ---
-        if rank == 0:
+        # (this and the two sections after it are single-GPU quantities: reported at N = 1 only)
+        if rank == 0 and world == 1:
             g = torch.Generator(device="cpu").manual_seed(1)
             base = torch.rand(1 << 18, 52, generator=g).argsort(1)[:, :7].numpy().astype(np.uint8)
             masks = torch.from_numpy(phe.ids_to_masks(base)).to(dev).repeat(128)
