@@ -342,13 +342,17 @@ k_attention(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict
     asm volatile("cp.async.commit_group;" ::: "memory");
     for (int it = 0; bh < total_bh; bh += gridDim.x, it++) {
         const int st = it & 1;
+        // One barrier per pair: the copies of this stage were issued an iteration ago (a whole MMA phase to land), and
+        // once every warp is past the barrier nobody still reads the other stage, so the next pair's copies go there.
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
         if (bh + (int)gridDim.x < total_bh) issue(bh + gridDim.x, st ^ 1);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncthreads();
         const uint32_t a_k = (uint32_t)__cvta_generic_to_shared(sm + 3 * st * kTile), a_v = a_k + 2u * kTile, a_q = a_k + 4u * kTile;
         const int b = bh / heads, h = bh - b * heads;
-        for (int qt = warp; qt < q_tiles; qt += kAttnWarps) {
+        // 98 rows are 7 tiles for 8 warps: the idle slot rotates (per iteration and per CTA) so that the tensor pipe of
+        // every scheduler gets the same share -- with a fixed map the scheduler of warp 7 ran at half load
+        for (int qt = (warp + it + (int)blockIdx.x) & (kAttnWarps - 1); qt < q_tiles; qt += kAttnWarps) {
             // ---- S = Q K^T ----
             uint32_t aq[KS][4];
 #pragma unroll
@@ -428,7 +432,6 @@ k_attention(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict
                 if (r1 < s_q) *reinterpret_cast<uint32_t*>(ob + (int64_t)r1 * heads * D + dt * 8 + 2 * t) = pack_bf16(o[dt][2] * inv1, o[dt][3] * inv1);
             }
         }
-        __syncthreads();           // every warp is done with this stage before the next iteration's copies overwrite it
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
