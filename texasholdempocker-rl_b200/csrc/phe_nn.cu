@@ -253,14 +253,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
-__device__ __forceinline__ void ldmatrix_x2(uint32_t (&r)[2], uint32_t addr)
-{
-    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
-}
-__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], uint32_t addr)
-{
-    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
-}
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
 {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -304,7 +296,6 @@ k_attention(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict
     __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(attn_smem);          // stage st: K at (3 st) kTile, V at (3 st + 1) kTile, Q at (3 st + 2) kTile
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q_tiles = (s_q + 15) >> 4;
-    const int q_rows = q_tiles * 16;
     // rows beyond the sequence stay zero for the whole launch (the copies below never touch them)
     for (int i = tid; i < 2 * kAttnMaxKeys * VPR; i += blockDim.x) {
         const int st = i / (kAttnMaxKeys * VPR), j = i - st * (kAttnMaxKeys * VPR);
