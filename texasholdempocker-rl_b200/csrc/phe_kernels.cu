@@ -1197,9 +1197,14 @@ int phe_enum7_host(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin, uin
     uint64_t* d7 = d9 + 9;
     PHE_CUDA(cudaMemsetAsync(t_out.p, 0, bytes, 0));
     if ((rc = phe_enum7(d9, d7, comb_begin, comb_end, nullptr))) return rc;
-    std::vector<uint64_t> tmp(9 + kHistBins);
-    PHE_CUDA(cudaMemcpyAsync(tmp.data(), t_out.p, bytes, cudaMemcpyDeviceToHost, 0));
+    // the 59,776-byte result comes back through the per-thread pinned buffer: a pageable destination would add a
+    // staging copy inside the driver to a call that is only ~0.2 ms long
+    static_assert((9 + kHistBins) * 8 <= kPinnedBytes, "histograms fit the pinned buffer");
+    unsigned char* pin;
+    if ((rc = t_pin.get(&pin))) return rc;
+    PHE_CUDA(cudaMemcpyAsync(pin, t_out.p, bytes, cudaMemcpyDeviceToHost, 0));
     PHE_CUDA(cudaStreamSynchronize(0));
+    const uint64_t* tmp = reinterpret_cast<const uint64_t*>(pin);
     if (hist9) for (int i = 0; i < 9; i++) hist9[i] += tmp[i];
     if (hist7463) for (int i = 0; i < kHistBins; i++) hist7463[i] += tmp[9 + i];
     return PHE_OK;

@@ -5,7 +5,9 @@ import texasholdempocker_rl_b200 as phe
 pv = phe.policy_value
 from torch.profiler import profile, ProfilerActivity
 m = pv.fill_parameters(pv.PolicyValueNet(**pv.DEFAULT_MODEL_PARAMS), 1).cuda().to(torch.bfloat16).eval()
-obs = torch.from_numpy(pv.random_observations(1024, seed=3)).cuda()
+import sys
+BATCH = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+obs = torch.from_numpy(pv.random_observations(BATCH, seed=3)).cuda()
 with torch.no_grad():
     for _ in range(3): m.policy_value(obs)
     torch.cuda.synchronize()

@@ -66,8 +66,6 @@ tile = lambda a: torch.from_numpy(np.tile(a, (rg,) + (1,) * (a.ndim - 1))[:B]).t
 sargs = [tile(a) for a in (boards, holes, act, val, nr, bt, ob)]
 want_won = np.tile(np.array([g["won"] for g in games], np.int32), (rg, 1))[:B]
 
-known = torch.from_numpy(np.tile(phe.ids_to_masks(np.array([[r["hand"] + (r["flop"] or []) + (r["turn"] or []) + (r["river"] or [])][0] + [0] * 0 for r in recs[:1]])), B)).to(dev) \
-    if False else None
 hero_board = [np.array(r["hand"] + (r["flop"] or []) + (r["turn"] or []) + (r["river"] or []), dtype=np.int64) for r in recs]
 # re-deals: heads-up pre-flop roots (need 2 + 5 = 7 cards), the most expensive determinisation
 pre = [hb for hb in hero_board if len(hb) == 2]
