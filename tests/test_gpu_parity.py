@@ -430,3 +430,33 @@ def test_deal_on_garbage_input_terminates(phe, torch):
     out = phe.deal(known, 9, seed=1)
     torch.cuda.synchronize()
     assert out.shape == (2, 9)
+
+
+def test_eval7_inside_a_cuda_graph(phe, oracle, torch):
+    """The batched evaluator is launched with programmatic stream serialisation (PDL); it must also capture into and
+    replay from a CUDA graph, after a copy node, after another kernel node and after itself."""
+    ids = rand_hands(1 << 17, 21)
+    want = oracle.rank7_batch(ids)
+    src = torch.from_numpy(phe.ids_to_masks(ids)).cuda()
+    masks = torch.empty_like(src)
+    out = torch.empty(src.shape[0], dtype=torch.int16, device="cuda")
+    out2 = torch.empty_like(out)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        masks.copy_(src)
+        phe.eval7(masks, out=out)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        masks.copy_(src)                 # copy node -> evaluator
+        phe.eval7(masks, out=out)
+        masks.add_(0)                    # kernel node -> evaluator -> evaluator
+        phe.eval7(masks, out=out2)
+        phe.eval7(masks, out=out)
+    out.zero_(); out2.zero_()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert (out.cpu().numpy().astype(np.uint16) == want).all() and (out2.cpu().numpy().astype(np.uint16) == want).all()
