@@ -220,6 +220,14 @@ int phe_nn_attention(const void *q, const void *k, const void *v, void *out, int
                      int s_kv, int head_dim, int64_t q_batch_stride, int64_t q_row_stride, int64_t kv_batch_stride,
                      int64_t kv_row_stride, int dtype, void *stream);
 
+/* What SingleThreadMCTS.predict consumes (rl/MCTS.py:464-473) from the encoder rows of tokens 0 and 1:
+ * out[b][0..n_actions) = softmax(action_prob_dense(h[b][0])), out[b][n_actions] = reward_value_dense(h[b][1]), fp32.
+ * h [batch][2][row_stride >= d]; weights as nn.Linear stores them (w_policy [n_actions][d], w_value [1][d]);
+ * n_actions <= 32. */
+int phe_nn_policy_value_heads(const void *h, const void *w_policy, const void *b_policy, const void *w_value,
+                              const void *b_value, float *out, int64_t batch, int d, int n_actions,
+                              int64_t row_stride, int dtype, void *stream);
+
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
 uint64_t phe_launch_count(void);
 

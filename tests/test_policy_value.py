@@ -217,3 +217,24 @@ def test_attention_kernel_gpu(H, D, Sq, S):
     want = want.transpose(1, 2).reshape(B, Sq, H * D)
     assert got.shape == want.shape and got.dtype == torch.bfloat16
     np.testing.assert_allclose(got.float().cpu().numpy(), want.cpu().numpy(), atol=2e-2, rtol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1.5e-2)])
+@pytest.mark.parametrize("B", [1, 3, 64, 1000])
+def test_policy_value_heads_kernel_gpu(golden, dtype, tol, B):
+    """phe_nn_policy_value_heads against the PyTorch expression it replaces (Linear + softmax, Linear) on the same
+    encoder rows, computed in fp32 from the same (rounded) weights."""
+    m = _model(golden[0]).to("cuda", dtype).eval()
+    g = torch.Generator(device="cpu").manual_seed(B)
+    h = torch.randn(B, 2, m.d_model, generator=g).to(dtype).cuda()
+    before = phe._native.launch_count()
+    with torch.no_grad():
+        out = m.policy_value_packed(h)
+        wp = torch.softmax(h[:, 0].float() @ m.action_prob_dense.weight.float().t() + m.action_prob_dense.bias.float(), dim=1)
+        wv = h[:, 1].float() @ m.reward_value_dense.weight.float().t() + m.reward_value_dense.bias.float()
+    assert phe._native.launch_count() == before + 1
+    assert out.dtype == torch.float32 and out.shape == (B, 13)
+    np.testing.assert_allclose(out[:, :12].cpu().numpy(), wp.cpu().numpy(), atol=tol, rtol=0)
+    np.testing.assert_allclose(out[:, 12].cpu().numpy(), wv[:, 0].cpu().numpy(), atol=tol * 4, rtol=0)
+    np.testing.assert_allclose(out[:, :12].sum(1).cpu().numpy(), 1.0, atol=1e-5)

@@ -23,7 +23,7 @@ SYMBOLS = [
     "phe_eval7", "phe_eval7_host", "phe_enum7", "phe_enum7_host", "phe_enum7_part", "phe_enum7_allreduce_workspace", "phe_enum7_allreduce",
     "phe_equity_mc", "phe_equity_mc_host", "phe_equity_plan", "phe_equity_plan_host", "phe_plan_num_deals",
     "phe_showdown", "phe_showdown_host", "phe_deal", "phe_deal_host", "phe_settle", "phe_settle_host", "phe_launch_count",
-    "phe_nn_add_layernorm", "phe_nn_embed_obs", "phe_nn_attention", "phe_obs_num_fields", "phe_obs_cut_table_bytes", "phe_encode_obs",
+    "phe_nn_add_layernorm", "phe_nn_embed_obs", "phe_nn_attention", "phe_nn_policy_value_heads", "phe_obs_num_fields", "phe_obs_cut_table_bytes", "phe_encode_obs",
 ]
 
 
@@ -72,6 +72,7 @@ def lib():
     L.phe_obs_cut_table_bytes.argtypes = []; L.phe_obs_cut_table_bytes.restype = u64
     L.phe_encode_obs.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, vp]; L.phe_encode_obs.restype = i32
     L.phe_nn_attention.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i64, i64, i64, i64, i32, vp]; L.phe_nn_attention.restype = i32
+    L.phe_nn_policy_value_heads.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i32, i64, i32, vp]; L.phe_nn_policy_value_heads.restype = i32
     L.phe_nn_embed_obs.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp]; L.phe_nn_embed_obs.restype = i32
     _lib = L
     return L

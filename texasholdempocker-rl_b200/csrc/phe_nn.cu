@@ -427,7 +427,80 @@ k_attention(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// phe_nn_policy_value_heads: what SingleThreadMCTS.predict reads (rl/MCTS.py:464-473) from encoder rows 0 and 1:
+// out[b] = { softmax(W_p h[b][0] + b_p) (A values), w_v . h[b][1] + b_v } as fp32.  One warp per observation; replaces
+// two GEMV launches, the softmax, two casts and two strided copies (eight ~3 us kernels in the small-batch regime the
+// reference runs in).
+// ---------------------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(128)
+k_policy_value_heads(const T* __restrict__ h, const T* __restrict__ wp, const T* __restrict__ bp, const T* __restrict__ wv,
+                     const T* __restrict__ bv, float* __restrict__ out, int64_t batch, int d, int n_actions, int64_t row_stride)
+{
+    constexpr int N = Vec<T>::N;
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= batch) return;
+    const T* h0 = h + b * 2 * row_stride;
+    const T* h1 = h0 + row_stride;
+    const int nvec = d / N;
+    float logit = -INFINITY;                 // lane a keeps logit a (n_actions <= 32)
+    for (int a = 0; a <= n_actions; a++) {   // a == n_actions: the value head on row 1
+        const T* w = a < n_actions ? wp + (int64_t)a * d : wv;
+        const T* x = a < n_actions ? h0 : h1;
+        float acc = 0.f;
+        for (int j = lane; j < nvec; j += 32) {
+            float xv[N], wvv[N];
+            Vec<T>::load(x + j * N, xv);
+            Vec<T>::load(w + j * N, wvv);
+#pragma unroll
+            for (int i = 0; i < N; i++) acc += xv[i] * wvv[i];
+        }
+        acc = warp_sum(acc);
+        if (a < n_actions) {
+            float bias[1];
+            bias[0] = sizeof(T) == 2 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(bp)[a]) : reinterpret_cast<const float*>(bp)[a];
+            // the reference's Linear output is rounded to the compute dtype before the fp32 softmax
+            float z = acc + bias[0];
+            if (sizeof(T) == 2) z = __bfloat162float(__float2bfloat16_rn(z));
+            if (lane == a) logit = z;
+        } else if (lane == 0) {
+            float z = acc + (sizeof(T) == 2 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(bv)[0]) : reinterpret_cast<const float*>(bv)[0]);
+            if (sizeof(T) == 2) z = __bfloat162float(__float2bfloat16_rn(z));
+            out[b * (n_actions + 1) + n_actions] = z;
+        }
+    }
+    float m = logit;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    const float e = lane < n_actions ? expf(logit - m) : 0.f;
+    const float ssum = warp_sum(e);
+    if (lane < n_actions) out[b * (n_actions + 1) + lane] = e / ssum;
+}
+
 }  // namespace
+
+extern "C" int phe_nn_policy_value_heads(const void* h, const void* w_policy, const void* b_policy, const void* w_value, const void* b_value,
+                                         float* out, int64_t batch, int d, int n_actions, int64_t row_stride, int dtype, void* stream)
+{
+    if (batch < 0 || d <= 0 || n_actions <= 0 || n_actions > 32 || (dtype != PHE_DTYPE_F32 && dtype != PHE_DTYPE_BF16)) return PHE_EINVAL;
+    if (batch == 0) return PHE_OK;
+    if (!h || !w_policy || !b_policy || !w_value || !b_value || !out) return PHE_EINVAL;
+    const int esz = dtype == PHE_DTYPE_BF16 ? 2 : 4;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(w_policy) | reinterpret_cast<uintptr_t>(w_value);
+    if ((al & 15) || (d * esz) % 16 || (row_stride * esz) % 16) return PHE_EINVAL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned blocks = (unsigned)((batch + 3) / 4);
+    if (dtype == PHE_DTYPE_BF16)
+        k_policy_value_heads<__nv_bfloat16><<<blocks, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(h), static_cast<const __nv_bfloat16*>(w_policy),
+                                                                     static_cast<const __nv_bfloat16*>(b_policy), static_cast<const __nv_bfloat16*>(w_value),
+                                                                     static_cast<const __nv_bfloat16*>(b_value), out, batch, d, n_actions, row_stride);
+    else
+        k_policy_value_heads<float><<<blocks, 128, 0, st>>>(static_cast<const float*>(h), static_cast<const float*>(w_policy), static_cast<const float*>(b_policy),
+                                                             static_cast<const float*>(w_value), static_cast<const float*>(b_value), out, batch, d, n_actions, row_stride);
+    return nn_after_launch();
+}
 
 extern "C" int phe_nn_attention(const void* q, const void* k, const void* v, void* out, int64_t batch, int heads, int s_q, int s_kv,
                                 int head_dim, int64_t q_batch_stride, int64_t q_row_stride, int64_t kv_batch_stride, int64_t kv_row_stride,

@@ -265,7 +265,25 @@ class PolicyValueNet(nn.Module):
     def policy_value(self, x):
         """What MCTS consumes (rl/MCTS.py:464-473): softmax action probabilities float32[B, A] and value float32[B]."""
         h = self.encode(x, n_out=2)
+        out = self.policy_value_packed(h)
+        if out is not None:
+            return out[:, : self.num_output_class], out[:, self.num_output_class]
         return (torch.softmax(self.action_prob_dense(h[:, 0]).float(), dim=1), self.reward_value_dense(h[:, 1]).squeeze(1).float())
+
+    def policy_value_packed(self, h, out=None):
+        """Encoder rows [B, 2, d] -> float32 [B, A + 1] (probabilities, then the value) in one kernel
+        (phe_nn_policy_value_heads); None when the tensors are not on the device / not a supported type."""
+        w = self.action_prob_dense.weight
+        if not (h.is_cuda and h.dtype in _DTYPES and w.dtype == h.dtype and self.num_output_class <= 32 and (self.d_model * h.element_size()) % 16 == 0):
+            return None
+        h = h.contiguous()
+        B = h.shape[0]
+        if out is None:
+            out = torch.empty((B, self.num_output_class + 1), dtype=torch.float32, device=h.device)
+        N.check(N.lib().phe_nn_policy_value_heads(_ptr(h), _ptr(w), _ptr(self.action_prob_dense.bias), _ptr(self.reward_value_dense.weight),
+                                                  _ptr(self.reward_value_dense.bias), _ptr(out), B, self.d_model, self.num_output_class,
+                                                  self.d_model, _DTYPES[h.dtype], _stream()))
+        return out
 
     def check_observations(self, x):
         """ValueError if an observation would index outside the embedding table.
@@ -333,9 +351,11 @@ class BatchedPredictor:
             out = torch.empty((b, self.n_actions + 1), dtype=torch.float32, device=self.device)
 
             def step():
-                p, v = self.model.policy_value(x)
-                out[:, : self.n_actions] = p
-                out[:, self.n_actions] = v
+                h = self.model.encode(x, n_out=2)
+                if self.model.policy_value_packed(h, out=out) is None:         # not reached on a CUDA device with f32 / bf16 weights
+                    p, v = self.model.policy_value(x)
+                    out[:, : self.n_actions] = p
+                    out[:, self.n_actions] = v
 
             with torch.no_grad(), torch.cuda.stream(self._stream):
                 for _ in range(3):          # warm up allocator, cuBLAS handles and attention kernel selection
