@@ -276,15 +276,26 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
 // two-stage shared-memory pipeline: the cp.async copies of the next pair are in flight while the current one is in the
 // MMA phase -- with one-shot CTAs the load and MMA phases of the four resident CTAs alternated and the kernel ran at
 // half of the memory rate.
+#ifndef PHE_ATTN_STAGES
+#define PHE_ATTN_STAGES 2      // 2: persistent CTAs, next pair prefetched; 1: one CTA per pair (grid = pairs)
+#endif
+
 template <int D>
 struct AttnSmem {
     static constexpr int LD = D + 8;
     static constexpr int kTile = kAttnMaxKeys * LD;            // elements of one K / V / Q tile
-    static constexpr uint32_t kBytes = 2u * 3u * kTile * 2u;   // two stages of {K, V, Q}
+    static constexpr uint32_t kBytes = PHE_ATTN_STAGES * 3u * kTile * 2u;   // stages of {K, V, Q}
 };
 
+#ifndef PHE_ATTN_GRID_PER_SM
+#define PHE_ATTN_GRID_PER_SM 2
+#endif
+#ifndef PHE_ATTN_MIN_CTAS
+#define PHE_ATTN_MIN_CTAS 2
+#endif
+
 template <int D>
-__global__ void __launch_bounds__(kAttnWarps * 32, 2)
+__global__ void __launch_bounds__(kAttnWarps * 32, PHE_ATTN_MIN_CTAS)
 k_attention(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
             __nv_bfloat16* __restrict__ out, int total_bh, int heads, int s_q, int s_kv, int64_t q_bs, int64_t q_rs, int64_t kv_bs,
             int64_t kv_rs, float scale_log2e)
@@ -297,7 +308,7 @@ k_attention(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q_tiles = (s_q + 15) >> 4;
     // rows beyond the sequence stay zero for the whole launch (the copies below never touch them)
-    for (int i = tid; i < 2 * kAttnMaxKeys * VPR; i += blockDim.x) {
+    for (int i = tid; i < PHE_ATTN_STAGES * kAttnMaxKeys * VPR; i += blockDim.x) {
         const int st = i / (kAttnMaxKeys * VPR), j = i - st * (kAttnMaxKeys * VPR);
         const int r = j / VPR, c = j - r * VPR;
         __nv_bfloat16* base = sm + 3 * st * kTile + r * LD + c * 8;
@@ -518,7 +529,7 @@ extern "C" int phe_nn_attention(const void* q, const void* k, const void* v, voi
     const int total = (int)(batch * heads);
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const unsigned blocks = (unsigned)(total < 2 * sms ? total : 2 * sms);
+    const unsigned blocks = (unsigned)(total < PHE_ATTN_GRID_PER_SM * sms ? total : PHE_ATTN_GRID_PER_SM * sms);
     static std::once_flag attr_once[16];
     std::call_once(attr_once[dev & 15], [] {
         cudaFuncSetAttribute(k_attention<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<64>::kBytes);
