@@ -284,6 +284,15 @@ def main():
                                "model_lane_ops_per_rollout": w_roll,
                                "roofline_frac_nominal": mc_val * w_roll / (NOMINAL_INT_PEAK * world),
                                "checksum": int(wtl[:, 0].sum().item())}
+        if rank == 0 and world == 1:
+            # the same batch end to end through the host-buffer API: numpy states in (H2D), numpy counts out (D2H)
+            hstates = phe.random_states(4096, 20261019)
+            t0 = time.perf_counter()
+            hw = phe.equity_mc(hstates, 5, R, seed=0x5EED20261019)
+            mdt = time.perf_counter() - t0
+            assert int(hw[:, 0].sum()) == extras["equity_mc"]["checksum"]
+            extras["equity_mc"]["e2e"] = {"value": 4096 * R / mdt, "unit": "rollouts/s", "h2d_bytes_per_step": int(hstates.nbytes),
+                                          "d2h_bytes_per_step": int(hw.nbytes)}
         # --- materialised-hands micro-config: 2^25 card sets (268 MB > L2) -> ranks ---
         # (this and the two sections after it are single-GPU quantities: reported at N = 1 only)
         if rank == 0 and world == 1:
