@@ -232,6 +232,12 @@ struct LocalSlots {             // host / small kernels: accepted slots kept in 
     PHE_HD uint64_t get_single() const { return single; }
     template <class DealTab>
     PHE_HD uint64_t get_pair(int k, const DealTab&) const { return pair[k]; }
+    // cursor over the pair slots: an index here, a shared-memory address in the kernels' slot store
+    typedef int cursor;
+    PHE_HD cursor cursor_at(int k) const { return k; }
+    PHE_HD cursor cursor_next(cursor c) const { return c + 1; }
+    PHE_HD int cursor_index(cursor c) const { return c; }
+    PHE_HD void put_at(cursor c, uint32_t q, uint64_t m) { put_pair(c, q, m); }
 };
 
 // returns the number of pair slots accepted (== n_pairs unless the input was malformed)
@@ -261,29 +267,33 @@ PHE_UNROLL
             }
         }
     }
-    int got = 0;
+    // the number of accepted pairs is kept as a cursor into the slot store (an address in the kernels): the accept path
+    // is one store and one add, with no index-to-address multiply
+    typename Slots::cursor cur = out.cursor_at(0);
+    const typename Slots::cursor end = out.cursor_at(n_pairs);
     int first_word = want_single ? 1 : 0;
     // 64 blocks = 512 draws: never reached with a valid state; bounds the loop on garbage
-    for (uint32_t blk = 0; got < n_pairs && blk < 64u; blk++) {
+    for (uint32_t blk = 0; cur < end && blk < 64u; blk++) {
         if (blk) philox4x32_10(s_lo, s_hi, stream, blk, k_lo, k_hi, rnd);
 PHE_UNROLL
         for (int wi = 0; wi < 4; wi++) {
             if (wi < first_word) continue;
-            if (got >= n_pairs) break;
+            if (!(cur < end)) break;
 PHE_UNROLL
             for (int h = 0; h < 2; h++) {
                 const uint32_t r = (rnd[wi] >> (16 * h)) & 0xFFFFu;
                 const uint32_t q = mod1326_u16(r);
                 const uint64_t m = dt.mask(q);
-                if (r < DEAL_PAIR_LIMIT && !(m & used) && got < n_pairs) {
+                if (r < DEAL_PAIR_LIMIT && !(m & used) && cur < end) {
                     used |= m;
-                    out.put_pair(got, q, m);
-                    got++;
+                    out.put_at(cur, q, m);
+                    cur = out.cursor_next(cur);
                 }
             }
         }
         first_word = 0;
     }
+    const int got = out.cursor_index(cur);
     return got;
 }
 

@@ -530,6 +530,14 @@ struct SmemSlots {
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(q) : "r"(base + (uint32_t)k * stride) : "memory");
         return dt.mask(q);
     }
+    typedef uint32_t cursor;      // shared address of the next free cell of this thread's column
+    __device__ __forceinline__ cursor cursor_at(int k) const { return base + (uint32_t)k * stride; }
+    __device__ __forceinline__ cursor cursor_next(cursor c) const { return c + stride; }
+    __device__ __forceinline__ int cursor_index(cursor c) const { return (int)((c - base) / stride); }
+    __device__ __forceinline__ void put_at(cursor c, uint32_t q, uint64_t)
+    {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(c), "r"(q) : "memory");
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
