@@ -518,10 +518,6 @@ struct SmemSlots {
     uint32_t stride;   // bytes per row = 4 * blockDim.x
     uint64_t single;
     __device__ __forceinline__ void put_single(uint64_t m) { single = m; }
-    __device__ __forceinline__ void put_pair(int k, uint32_t q, uint64_t)
-    {
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + (uint32_t)k * stride), "r"(q) : "memory");
-    }
     __device__ __forceinline__ uint64_t get_single() const { return single; }
     template <class DealTab>
     __device__ __forceinline__ uint64_t get_pair(int k, const DealTab& dt) const
