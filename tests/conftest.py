@@ -45,3 +45,19 @@ def hostcheck():
     L.hc_plan_num_deals.argtypes = [C.c_int, vp, C.c_int]
     L.hc_plan_num_deals.restype = C.c_uint64
     return L
+
+
+@pytest.fixture(scope="session")
+def reference_tree():
+    """sys.path set up for the UNMODIFIED reference checkout in baseline/_ref (made from /root/reference by
+    baseline/make_ref.py when it is missing; it ships to the GPU box) + the phevaluator shim.  Skips when neither exists."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_ref", os.path.join(ROOT, "baseline", "make_ref.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    if not os.path.exists(os.path.join(mk.DST, "MANIFEST.json")) and mk.make() is None:
+        pytest.skip("no reference checkout (baseline/_ref absent and /root/reference not present)")
+    for p in reversed(mk.paths()):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    return mk.DST

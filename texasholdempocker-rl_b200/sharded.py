@@ -30,11 +30,21 @@ def _world(group):
 def sharded_equity_mc(states, n_opp, rollouts, seed, sample_offset=0, group=None, local_fn=None, reduce=True):
     """Every rank holds the same `states`; rank r rolls samples shard_range(rollouts, r, world) and the
     (win, tie, loss) counts are all-reduced.  local_fn(states, n_opp, rollouts, seed, sample_offset=...)
-    defaults to the CUDA path (tests inject the oracle there)."""
+    defaults to the CUDA path (tests inject the oracle there).
+
+    Host arrays in -> host array out on every rank: with the NCCL backend the states go to the device once
+    (H2D), the shard is rolled there, the int64[S,3] counts are all-reduced over NVLink and copied back (D2H)."""
     from .equity import equity_mc
     fn = local_fn or equity_mc
     rank, world = _world(group)
     b, e = shard_range(rollouts, rank, world)
+    on_host = not (torch is not None and isinstance(states, torch.Tensor))
+    if on_host and local_fn is None and world > 1 and reduce and dist.get_backend(group) == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = torch.from_numpy(np.ascontiguousarray(states, dtype=np.int64)).to(dev, non_blocking=True)
+        counts = equity_mc(t, n_opp, e - b, seed, sample_offset=sample_offset + b)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+        return counts.cpu().numpy()
     counts = fn(states, n_opp, e - b, seed, sample_offset=sample_offset + b)
     if world > 1 and reduce:
         t = counts if (torch is not None and isinstance(counts, torch.Tensor)) else torch.from_numpy(np.ascontiguousarray(counts))
