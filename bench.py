@@ -212,7 +212,7 @@ def reference_arm(args):
         else:
             st = random_states(S, STATE_SEED + (1 if args.config == 5 else 0)).view(np.uint64)
             n_opp = MC_PLAYERS - 1
-            per_state = max(1, round(12000 * cores / S))                  # ~1 s of work per step on this box's cores
+            per_state = max(1, round(45000 * cores / S))                  # ~1 s of work per step on this box's cores
             config = mc_config(max(1, args.gpus)) if args.config == 3 else {"workload": "sharded_mc_equity_sweep", "states": 64, "players": 6,
                                                                            "rollouts_per_state": 10**9}
         states = [(int(a), int(b)) for a, b in st]
@@ -652,7 +652,7 @@ def mcts_selfplay(phe, torch, n_simulation=800, moves=4):
     from env.constants import ChoiceMethod
     torch.set_num_threads(1)
     params, mp_, model, env = R.build_model_and_env()
-    net = phe.PolicyValueNet(**{k: mp_[k] for k in phe.policy_value.DEBUG_MODEL_PARAMS})
+    net = phe.PolicyValueNet(**mp_)
     net.load_reference_state_dict(model.state_dict())
     predictor = phe.BatchedPredictor(net, dtype=torch.float32, max_batch=64, buckets=[1, 8, 64])
     predictor.warmup()

@@ -152,6 +152,13 @@ int phe_deal(const uint64_t *known, int64_t n, int need, uint64_t seed, uint64_t
              uint32_t stream_base, uint8_t *cards_out, void *stream);
 int phe_deal_host(const uint64_t *known, int64_t n, int need, uint64_t seed, uint64_t sample_offset,
                   uint32_t stream_base, uint8_t *cards_out);
+/* Same deal routine, rows numbered along the SAMPLE axis: row i is sample (sample_offset + i) of the one stream
+ * `stream_id`.  This is the form a caller with one logical stream (a game, a search tree) wants: n re-deals of
+ * GameEnv.new_random (env/game.py:119-163) are n consecutive samples, and two stream ids never share a deal. */
+int phe_deal_samples(const uint64_t *known, int64_t n, int need, uint64_t seed, uint64_t sample_offset,
+                     uint32_t stream_id, uint8_t *cards_out, void *stream);
+int phe_deal_samples_host(const uint64_t *known, int64_t n, int need, uint64_t seed, uint64_t sample_offset,
+                          uint32_t stream_id, uint8_t *cards_out);
 
 /* ---- terminal settlement (finish_game / _share_value, env/game.py:410-441, 560-632, 683-734) ---- */
 /* Per game: boards[g] (5-card set), holes[g][P] (2-card sets, every seat), actions[g][R][P] = last action of each

@@ -12,8 +12,11 @@ Inputs are plain arrays (seat order = the reference's players dict order):
   onboard[P]      status == ONBOARD at the end (used only by the odd-chip rule)
 Quirks kept on purpose: a player whose action in a round is None (all-in earlier -- or folded earlier, for more than
 two players) still contends in that round's showdowns (the reference tests `!= FOLD`, env/game.py:599, 625); the game
-result is the one written by the LAST showdown a player won (:553).  One fix: where the reference's odd-chip loop
-would not terminate (:731-733) the chips go to the first winner clockwise from the button.
+result is the one written by the LAST showdown a player won (:553).  Two fixes, both outside what the reference can
+compute (tables of more than two seats): (1) where its odd-chip loop would not terminate (:731-733) the chips go to
+the first winner clockwise from the button; (2) a final pot that is left without a contender -- every seat still in
+the hand was already settled as an all-in layer, the reference divides by an empty winner set (:721) -- goes to the
+best hand among the seats that have not folded.
 """
 from math import floor
 
@@ -96,7 +99,10 @@ def settle(ranks, actions, values, onboard, button, small_blind):
         pot += sum(spare.values())
     if pot > 0:
         last = actions[-1]
-        winners = winner_set(ranks, [p for p in players if last[p] != 1 and p not in all_shared])
+        contenders = [p for p in players if last[p] != 1 and p not in all_shared]
+        if not contenders:                  # the reference divides by an empty winner set here (:721); documented fix 2
+            contenders = [p for p in players if last[p] != 1]
+        winners = winner_set(ranks, contenders)
         _mark(winners, result)
         _pay(pot, winners, won, small_blind, button, onboard)
     cw = winner_set(ranks, players) if P > 1 else {0}

@@ -460,3 +460,31 @@ def test_eval7_inside_a_cuda_graph(phe, oracle, torch):
         g.replay()
     torch.cuda.synchronize()
     assert (out.cpu().numpy().astype(np.uint16) == want).all() and (out2.cpu().numpy().astype(np.uint16) == want).all()
+
+
+@pytest.mark.gpu
+def test_host_calls_do_not_wait_for_other_streams(phe, oracle, torch):
+    """SURVEY 8b "Threading": the *_host entry points run on a non-blocking stream owned by the calling thread and synchronise
+    only that stream.  A long kernel on torch's default (legacy NULL) stream -- what another game-loop thread or the predictor
+    may have in flight -- must not delay them: on the NULL stream they would queue behind it."""
+    import time
+    ids = rand_hands(64, 21)
+    want = oracle.rank7_batch(ids)
+    st = phe.pack_states([["As", "Ah"]], [["2c", "7d", "Tc"]])
+    phe.evaluate_cards(*ids[0].tolist())
+    phe.equity_mc(st, 1, 2000, seed=5)
+    torch.cuda.synchronize()
+    done = torch.cuda.Event()
+    torch.cuda._sleep(int(0.4 * 1.9e9))                 # ~0.4 s spin kernel on the default stream (one thread: leaves the SMs free)
+    done.record()
+    t0 = time.perf_counter()
+    for k in range(64):
+        assert phe.evaluate_cards(*ids[k].tolist()) == int(want[k])
+    assert (phe.eval7(ids) == want).all()
+    got = phe.equity_mc(st, 1, 2000, seed=5)
+    winners = phe.GameEnv.get_winner_set_v2(["2c", "7d", "Tc"], ["3h"], ["9s"], {"a": ["As", "Ah"], "b": ["Kd", "Kc"]})
+    dt = time.perf_counter() - t0
+    still_running = not done.query()
+    torch.cuda.synchronize()
+    assert winners == {"a"} and int(got.sum()) == 2000
+    assert still_running and dt < 0.2, f"host calls took {dt * 1e3:.1f} ms behind a 400 ms kernel on another stream (still running: {still_running})"

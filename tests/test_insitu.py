@@ -121,7 +121,7 @@ def test_reference_selfplay_on_all_dropins(reference_tree, phe):
     torch.set_num_threads(1)
     setup = _setup(reference_tree, 23)
     params, mp, model, env = setup
-    net = phe.PolicyValueNet(**{k: mp[k] for k in phe.policy_value.DEBUG_MODEL_PARAMS})
+    net = phe.PolicyValueNet(**mp)
     net.load_reference_state_dict(model.state_dict())
     predictor = phe.BatchedPredictor(net, dtype=torch.float32, max_batch=64)
     trace, log = _play(reference_tree, 23, setup, dropins=True, settle=True, predictor=predictor,
@@ -175,7 +175,7 @@ def test_wave_mcts_on_device_stages(reference_tree, phe, steps_before):
         mask, ranges, left, hist, dmin = env.get_valid_action_info_v2()
         obs, _, done, _ = env.step(map_action_bin_to_actual_action_and_value_v2(1, ranges, left, hist, dmin, 25), 1)
         assert not done
-    net = phe.PolicyValueNet(**{k: mp[k] for k in phe.policy_value.DEBUG_MODEL_PARAMS})
+    net = phe.PolicyValueNet(**mp)
     net.load_reference_state_dict(model.state_dict())
     backends = _SnapshotBackends(GpuBackends(phe.BatchedPredictor(net, dtype=torch.float32, max_batch=64),
                                              phe.ObsEncoder(mp["num_output_class"], mp["historical_action_per_round"]), seed=99))

@@ -147,6 +147,31 @@ def test_predictor_threads_gpu(golden):
 
 
 @pytest.mark.gpu
+def test_predictor_follows_weight_updates_gpu(golden):
+    """The reference's predict_batch_process reloads weights while it serves (update_model_param_queue, env/workflow.py:274-593).
+    Captured graphs hold the folded embedding tables by address: an update -- through the predictor or in place behind its
+    back -- must reach the replays (tables refolded into the same storage), checked against a fresh fp32 module."""
+    obs = pv.random_observations(48, seed=3)
+    pred = pv.BatchedPredictor(pv.fill_parameters(pv.PolicyValueNet(**pv.DEBUG_MODEL_PARAMS), 1), dtype=torch.float32, max_batch=64)
+    pred.warmup()
+    graphs = dict(pred._graphs)
+
+    def want(seed):
+        with torch.no_grad():
+            p, v = pv.fill_parameters(pv.PolicyValueNet(**pv.DEBUG_MODEL_PARAMS), seed).eval().policy_value(torch.from_numpy(obs))
+        return p.numpy(), v.numpy()
+    for seed, how in ((1, None), (2, "api"), (3, "in_place"), (4, "api")):
+        if how == "api":
+            pred.load_reference_state_dict(pv.fill_parameters(pv.PolicyValueNet(**pv.DEBUG_MODEL_PARAMS), seed).state_dict())
+        elif how == "in_place":
+            pv.fill_parameters(pred.model, seed)
+        p, v = pred.predict_batch(obs)
+        wp, wv = want(seed)
+        assert np.abs(p - wp).max() < 1e-3 and np.abs(v - wv).max() < 2e-3, f"stale weights after update {seed} ({how})"
+    assert all(pred._graphs[b][0] is g[0] for b, g in graphs.items()), "graphs were re-captured although the tables kept their storage"
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("rows,d", [(1, 96), (37, 96), (1000, 640), (333, 2048 if True else 0), (5, 8), (64, 1024)])
 def test_add_layernorm_kernel_gpu(dtype, rows, d):
@@ -217,6 +242,28 @@ def test_attention_kernel_gpu(H, D, Sq, S):
     want = want.transpose(1, 2).reshape(B, Sq, H * D)
     assert got.shape == want.shape and got.dtype == torch.bfloat16
     np.testing.assert_allclose(got.float().cpu().numpy(), want.cpu().numpy(), atol=2e-2, rtol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shift", [-40.0, -200.0, 30.0])
+def test_attention_kernel_strongly_shifted_logits_gpu(shift):
+    """Softmax is shift invariant, so a checkpoint may produce rows whose real logits are all far below zero (or far above).
+    Padded key columns (98 -> 112) must not take part in the row maximum or the row sum: every query row sees logits
+    q.k/sqrt(D) = shift + noise here (a constant component in q and k), against PyTorch's SDPA in fp32."""
+    B, H, D, S = 5, 10, 64, 98
+    g = torch.Generator(device="cpu").manual_seed(int(abs(shift)))
+    q = torch.randn(B, S, H, D, generator=g) * 0.3
+    k = torch.randn(B, S, H, D, generator=g) * 0.3
+    v = torch.randn(B, S, H, D, generator=g)
+    a = (abs(shift) * D ** 0.5) ** 0.5                       # q0 * k0 / sqrt(D) = shift on the first dimension
+    q[..., 0] = a
+    k[..., 0] = a if shift > 0 else -a
+    q, k, v = (t.to(torch.bfloat16).cuda().contiguous() for t in (q, k, v))
+    got = pv._attention(q, k, v)
+    want = torch.nn.functional.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2), v.float().transpose(1, 2))
+    want = want.transpose(1, 2).reshape(B, S, H * D)
+    assert torch.isfinite(got.float()).all()
+    np.testing.assert_allclose(got.float().cpu().numpy(), want.cpu().numpy(), atol=3e-2, rtol=0)
 
 
 @pytest.mark.gpu

@@ -88,3 +88,22 @@ def test_gpu_determinise_matches_reference_distribution(phe, oracle, gi):
     raw = phe.deal(np.full(4, known, dtype=np.int64), need, 11 + gi)
     for i in range(4):
         assert (raw[i] == oracle.deal(known, 11 + gi, 0, i, need)).all()
+
+
+@pytest.mark.gpu
+def test_gpu_determinise_streams_are_disjoint_and_follow_the_oracle(phe, oracle):
+    """Re-deal i of determinise(stream=s) is sample (offset + i) of Philox stream s (phe_deal_samples): equal to the oracle's
+    deal for that (stream, sample), and two callers numbering their trees s and s + 1 share no (stream, sample) pair."""
+    hero, shown = ["As", "Ah"], ["2c", "7d", "Tc"]
+    known = phe.cards_to_mask(hero + shown)
+    a = phe.deal(np.full(64, known, dtype=np.int64), 4, 5, sample_offset=10, stream_base=7, by_sample=True)
+    b = phe.deal(np.full(64, known, dtype=np.int64), 4, 5, sample_offset=10, stream_base=8, by_sample=True)
+    for i in range(0, 64, 7):
+        assert a[i].tolist() == oracle.deal(known, 5, 10 + i, 7, 4)
+        assert b[i].tolist() == oracle.deal(known, 5, 10 + i, 8, 4)
+    assert (a != b).any(axis=1).sum() >= 60                       # adjacent streams: independent deals, not a shifted copy
+    assert not any((a[i + 1] == b[i]).all() for i in range(63))  # (the old row = stream numbering made these identical)
+    o1, b1 = phe.determinise(hero, shown, 2, 16, seed=5, sample_offset=10, stream=7)
+    o2, b2 = phe.determinise(hero, shown, 2, 16, seed=5, sample_offset=26, stream=7)
+    o3, b3 = phe.determinise(hero, shown, 2, 32, seed=5, sample_offset=10, stream=7)
+    assert (np.concatenate([o1, o2]) == o3).all() and (np.concatenate([b1, b2]) == b3).all()       # waves tile the sample axis

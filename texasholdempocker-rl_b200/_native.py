@@ -22,7 +22,7 @@ SYMBOLS = [
     "phe_strerror", "phe_last_cuda_error", "phe_version", "phe_init",
     "phe_eval7", "phe_eval7_host", "phe_enum7", "phe_enum7_host", "phe_enum7_part", "phe_enum7_allreduce_workspace", "phe_enum7_allreduce",
     "phe_equity_mc", "phe_equity_mc_host", "phe_equity_plan", "phe_equity_plan_host", "phe_plan_num_deals",
-    "phe_showdown", "phe_showdown_host", "phe_deal", "phe_deal_host", "phe_settle", "phe_settle_host", "phe_launch_count",
+    "phe_showdown", "phe_showdown_host", "phe_deal", "phe_deal_host", "phe_deal_samples", "phe_deal_samples_host", "phe_settle", "phe_settle_host", "phe_launch_count",
     "phe_nn_add_layernorm", "phe_nn_embed_obs", "phe_nn_attention", "phe_nn_policy_value_heads", "phe_obs_num_fields", "phe_obs_cut_table_bytes", "phe_encode_obs",
 ]
 
@@ -64,6 +64,8 @@ def lib():
     L.phe_showdown_host.argtypes = [vp, vp, vp, i64, i32, vp, vp]; L.phe_showdown_host.restype = i32
     L.phe_deal.argtypes = [vp, i64, i32, u64, u64, u32, vp, vp]; L.phe_deal.restype = i32
     L.phe_deal_host.argtypes = [vp, i64, i32, u64, u64, u32, vp]; L.phe_deal_host.restype = i32
+    L.phe_deal_samples.argtypes = [vp, i64, i32, u64, u64, u32, vp, vp]; L.phe_deal_samples.restype = i32
+    L.phe_deal_samples_host.argtypes = [vp, i64, i32, u64, u64, u32, vp]; L.phe_deal_samples_host.restype = i32
     L.phe_settle.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp]; L.phe_settle.restype = i32
     L.phe_settle_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, vp, vp, vp]; L.phe_settle_host.restype = i32
     L.phe_launch_count.restype = u64

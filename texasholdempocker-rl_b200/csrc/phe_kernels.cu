@@ -826,12 +826,14 @@ k_showdown_gmem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict__
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_deal(const uint64_t* __restrict__ g_dealtab, const uint64_t* __restrict__ known, int64_t n, int need, uint64_t seed, uint64_t sample,
-       uint32_t stream_base, uint8_t* __restrict__ cards_out)
+       uint32_t stream_base, int by_sample, uint8_t* __restrict__ cards_out)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint8_t ids[MAX_DEAL];
-    deal_ids(GlobalDealTab{g_dealtab}, known[i] & CARD_BITS, seed, sample, stream_base + (uint32_t)i, need, ids);
+    // row i is either stream (stream_base + i) at one sample index, or sample (sample + i) of one stream
+    deal_ids(GlobalDealTab{g_dealtab}, known[i] & CARD_BITS, seed, by_sample ? sample + (uint64_t)i : sample,
+             by_sample ? stream_base : stream_base + (uint32_t)i, need, ids);
     for (int k = 0; k < need; k++) cards_out[i * need + k] = ids[k];
 }
 
@@ -862,7 +864,9 @@ k_settle(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict__ boards
     int32_t won[SETTLE_MAX_PLAYERS];
     int8_t res[SETTLE_MAX_PLAYERS], card[SETTLE_MAX_PLAYERS];
     uint32_t paid;
-    settle_game(P, nr, button[g], small_blind, onboard[g], ranks, act, val, won, res, card, &paid);
+    int bt = button[g];
+    bt = bt < 0 || bt >= P ? 0 : bt;      // caller memory is not trusted with an array index (the host layer rejects such rows)
+    settle_game(P, nr, bt, small_blind, onboard[g], ranks, act, val, won, res, card, &paid);
     for (int p = 0; p < P; p++) {
         won_out[g * P + p] = won[p];
         result_out[g * P + p] = res[p];
@@ -1022,6 +1026,28 @@ struct Pinned {
 };
 thread_local Pinned t_pin;
 
+// The *_host entry points run on a non-blocking stream owned by the calling host thread (one per thread and device) and
+// synchronise that stream only: game-loop threads neither serialise on the legacy NULL stream nor implicitly wait for the
+// predictor's or anybody else's blocking streams (SURVEY 8b "Threading").
+struct HostStream {
+    cudaStream_t s = nullptr;
+    int dev = -1;
+    int get(cudaStream_t* out)
+    {
+        int d = 0;
+        PHE_CUDA(cudaGetDevice(&d));
+        if (!s || d != dev) {
+            if (s) cudaStreamDestroy(s);
+            s = nullptr;
+            PHE_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            dev = d;
+        }
+        *out = s;
+        return PHE_OK;
+    }
+};
+thread_local HostStream t_hstream;
+
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
@@ -1102,21 +1128,23 @@ int phe_eval7_host(const void* hands, int layout, int64_t n, uint16_t* out)
     if (!hands || !out) return PHE_EINVAL;
     const size_t in_bytes = (size_t)n * (layout == PHE_LAYOUT_IDS ? 7 : 8);
     int rc;
+    cudaStream_t hs;
+    if ((rc = t_hstream.get(&hs))) return rc;
     if (align256(in_bytes) + (size_t)n * 2 <= kPinnedBytes) {
         unsigned char* pin;
         if ((rc = t_pin.get(&pin))) return rc;
         std::memcpy(pin, hands, in_bytes);
         uint16_t* res = reinterpret_cast<uint16_t*>(pin + align256(in_bytes));
-        if ((rc = phe_eval7(pin, layout, n, res, nullptr))) return rc;
-        PHE_CUDA(cudaStreamSynchronize(0));
+        if ((rc = phe_eval7(pin, layout, n, res, hs))) return rc;
+        PHE_CUDA(cudaStreamSynchronize(hs));
         std::memcpy(out, res, (size_t)n * 2);
         return PHE_OK;
     }
     if ((rc = t_in.ensure(in_bytes)) || (rc = t_out.ensure((size_t)n * 2))) return rc;
-    PHE_CUDA(cudaMemcpyAsync(t_in.p, hands, in_bytes, cudaMemcpyHostToDevice, 0));
-    if ((rc = phe_eval7(t_in.p, layout, n, static_cast<uint16_t*>(t_out.p), nullptr))) return rc;
-    PHE_CUDA(cudaMemcpyAsync(out, t_out.p, (size_t)n * 2, cudaMemcpyDeviceToHost, 0));
-    PHE_CUDA(cudaStreamSynchronize(0));
+    PHE_CUDA(cudaMemcpyAsync(t_in.p, hands, in_bytes, cudaMemcpyHostToDevice, hs));
+    if ((rc = phe_eval7(t_in.p, layout, n, static_cast<uint16_t*>(t_out.p), hs))) return rc;
+    PHE_CUDA(cudaMemcpyAsync(out, t_out.p, (size_t)n * 2, cudaMemcpyDeviceToHost, hs));
+    PHE_CUDA(cudaStreamSynchronize(hs));
     return PHE_OK;
 }
 
@@ -1195,19 +1223,21 @@ int phe_enum7_host(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin, uin
 {
     if (comb_begin > comb_end || comb_end > PHE_NUM_HANDS_7) return PHE_EINVAL;
     int rc;
+    cudaStream_t hs;
+    if ((rc = t_hstream.get(&hs))) return rc;
     const size_t bytes = (size_t)(9 + kHistBins) * 8;
     if ((rc = t_out.ensure(bytes))) return rc;
     uint64_t* d9 = static_cast<uint64_t*>(t_out.p);
     uint64_t* d7 = d9 + 9;
-    PHE_CUDA(cudaMemsetAsync(t_out.p, 0, bytes, 0));
-    if ((rc = phe_enum7(d9, d7, comb_begin, comb_end, nullptr))) return rc;
+    PHE_CUDA(cudaMemsetAsync(t_out.p, 0, bytes, hs));
+    if ((rc = phe_enum7(d9, d7, comb_begin, comb_end, hs))) return rc;
     // the 59,776-byte result comes back through the per-thread pinned buffer: a pageable destination would add a
     // staging copy inside the driver to a call that is only ~0.2 ms long
     static_assert((9 + kHistBins) * 8 <= kPinnedBytes, "histograms fit the pinned buffer");
     unsigned char* pin;
     if ((rc = t_pin.get(&pin))) return rc;
-    PHE_CUDA(cudaMemcpyAsync(pin, t_out.p, bytes, cudaMemcpyDeviceToHost, 0));
-    PHE_CUDA(cudaStreamSynchronize(0));
+    PHE_CUDA(cudaMemcpyAsync(pin, t_out.p, bytes, cudaMemcpyDeviceToHost, hs));
+    PHE_CUDA(cudaStreamSynchronize(hs));
     const uint64_t* tmp = reinterpret_cast<const uint64_t*>(pin);
     if (hist9) for (int i = 0; i < 9; i++) hist9[i] += tmp[i];
     if (hist7463) for (int i = 0; i < kHistBins; i++) hist7463[i] += tmp[9 + i];
@@ -1257,16 +1287,18 @@ int phe_equity_mc_host(const uint64_t* states, int64_t n_states, int n_opp, uint
     if (n_states == 0) return PHE_OK;
     if (!states || !wtl) return PHE_EINVAL;
     int rc;
+    cudaStream_t hs;
+    if ((rc = t_hstream.get(&hs))) return rc;
     const size_t in_bytes = (size_t)n_states * 16, out_bytes = (size_t)n_states * 24;
     if ((rc = t_in.ensure(in_bytes)) || (rc = t_out.ensure(out_bytes))) return rc;
-    PHE_CUDA(cudaMemcpyAsync(t_in.p, states, in_bytes, cudaMemcpyHostToDevice, 0));
-    PHE_CUDA(cudaMemsetAsync(t_out.p, 0, out_bytes, 0));
+    PHE_CUDA(cudaMemcpyAsync(t_in.p, states, in_bytes, cudaMemcpyHostToDevice, hs));
+    PHE_CUDA(cudaMemsetAsync(t_out.p, 0, out_bytes, hs));
     if ((rc = phe_equity_mc(static_cast<const uint64_t*>(t_in.p), n_states, n_opp, rollouts, sample_offset, seed, state_index_base,
-                            static_cast<uint64_t*>(t_out.p), nullptr)))
+                            static_cast<uint64_t*>(t_out.p), hs)))
         return rc;
     std::vector<uint64_t> tmp((size_t)n_states * 3);
-    PHE_CUDA(cudaMemcpyAsync(tmp.data(), t_out.p, out_bytes, cudaMemcpyDeviceToHost, 0));
-    PHE_CUDA(cudaStreamSynchronize(0));
+    PHE_CUDA(cudaMemcpyAsync(tmp.data(), t_out.p, out_bytes, cudaMemcpyDeviceToHost, hs));
+    PHE_CUDA(cudaStreamSynchronize(hs));
     for (size_t i = 0; i < tmp.size(); i++) wtl[i] += tmp[i];
     return PHE_OK;
 }
@@ -1327,16 +1359,18 @@ int phe_equity_plan_host(const uint8_t* exist, int n_exist, int64_t n_tasks, con
     if (n_tasks == 0) return PHE_OK;
     if (!exist || !wtl) return PHE_EINVAL;
     int rc;
+    cudaStream_t hs;
+    if ((rc = t_hstream.get(&hs))) return rc;
     const size_t in_bytes = (size_t)n_tasks * 8, out_bytes = (size_t)n_tasks * 24;
     if ((rc = t_in.ensure(in_bytes)) || (rc = t_out.ensure(out_bytes))) return rc;
-    PHE_CUDA(cudaMemcpyAsync(t_in.p, exist, in_bytes, cudaMemcpyHostToDevice, 0));
-    PHE_CUDA(cudaMemsetAsync(t_out.p, 0, out_bytes, 0));
+    PHE_CUDA(cudaMemcpyAsync(t_in.p, exist, in_bytes, cudaMemcpyHostToDevice, hs));
+    PHE_CUDA(cudaMemsetAsync(t_out.p, 0, out_bytes, hs));
     if ((rc = phe_equity_plan(static_cast<const uint8_t*>(t_in.p), n_exist, n_tasks, plan, n_steps, seed, stream_base,
-                              static_cast<uint64_t*>(t_out.p), nullptr)))
+                              static_cast<uint64_t*>(t_out.p), hs)))
         return rc;
     std::vector<uint64_t> tmp((size_t)n_tasks * 3);
-    PHE_CUDA(cudaMemcpyAsync(tmp.data(), t_out.p, out_bytes, cudaMemcpyDeviceToHost, 0));
-    PHE_CUDA(cudaStreamSynchronize(0));
+    PHE_CUDA(cudaMemcpyAsync(tmp.data(), t_out.p, out_bytes, cudaMemcpyDeviceToHost, hs));
+    PHE_CUDA(cudaStreamSynchronize(hs));
     for (size_t i = 0; i < tmp.size(); i++) wtl[i] += tmp[i];
     return PHE_OK;
 }
@@ -1374,6 +1408,8 @@ int phe_showdown_host(const uint64_t* boards, const uint64_t* holes, const uint3
     const size_t in_bytes = o_live + align256(G * 4);
     const size_t o_win = 0, o_ranks = align256(G * 4), out_bytes = o_ranks + align256(G * P * 2);
     int rc;
+    cudaStream_t hs;
+    if ((rc = t_hstream.get(&hs))) return rc;
     if (in_bytes + out_bytes <= kPinnedBytes) {
         unsigned char* pin;
         if ((rc = t_pin.get(&pin))) return rc;
@@ -1383,9 +1419,9 @@ int phe_showdown_host(const uint64_t* boards, const uint64_t* holes, const uint3
         unsigned char* po = pin + in_bytes;
         if ((rc = phe_showdown(reinterpret_cast<uint64_t*>(pin + o_boards), reinterpret_cast<uint64_t*>(pin + o_holes),
                                live ? reinterpret_cast<uint32_t*>(pin + o_live) : nullptr, n_games, n_players,
-                               reinterpret_cast<uint32_t*>(po + o_win), ranks_out ? reinterpret_cast<uint16_t*>(po + o_ranks) : nullptr, nullptr)))
+                               reinterpret_cast<uint32_t*>(po + o_win), ranks_out ? reinterpret_cast<uint16_t*>(po + o_ranks) : nullptr, hs)))
             return rc;
-        PHE_CUDA(cudaStreamSynchronize(0));
+        PHE_CUDA(cudaStreamSynchronize(hs));
         std::memcpy(winners_out, po + o_win, G * 4);
         if (ranks_out) std::memcpy(ranks_out, po + o_ranks, G * P * 2);
         return PHE_OK;
@@ -1393,16 +1429,16 @@ int phe_showdown_host(const uint64_t* boards, const uint64_t* holes, const uint3
     if ((rc = t_in.ensure(in_bytes)) || (rc = t_out.ensure(out_bytes))) return rc;
     char* di = static_cast<char*>(t_in.p);
     char* dout = static_cast<char*>(t_out.p);
-    PHE_CUDA(cudaMemcpyAsync(di + o_boards, boards, G * 8, cudaMemcpyHostToDevice, 0));
-    PHE_CUDA(cudaMemcpyAsync(di + o_holes, holes, G * P * 8, cudaMemcpyHostToDevice, 0));
-    if (live) PHE_CUDA(cudaMemcpyAsync(di + o_live, live, G * 4, cudaMemcpyHostToDevice, 0));
+    PHE_CUDA(cudaMemcpyAsync(di + o_boards, boards, G * 8, cudaMemcpyHostToDevice, hs));
+    PHE_CUDA(cudaMemcpyAsync(di + o_holes, holes, G * P * 8, cudaMemcpyHostToDevice, hs));
+    if (live) PHE_CUDA(cudaMemcpyAsync(di + o_live, live, G * 4, cudaMemcpyHostToDevice, hs));
     if ((rc = phe_showdown(reinterpret_cast<uint64_t*>(di + o_boards), reinterpret_cast<uint64_t*>(di + o_holes),
                            live ? reinterpret_cast<uint32_t*>(di + o_live) : nullptr, n_games, n_players,
-                           reinterpret_cast<uint32_t*>(dout + o_win), ranks_out ? reinterpret_cast<uint16_t*>(dout + o_ranks) : nullptr, nullptr)))
+                           reinterpret_cast<uint32_t*>(dout + o_win), ranks_out ? reinterpret_cast<uint16_t*>(dout + o_ranks) : nullptr, hs)))
         return rc;
-    PHE_CUDA(cudaMemcpyAsync(winners_out, dout + o_win, G * 4, cudaMemcpyDeviceToHost, 0));
-    if (ranks_out) PHE_CUDA(cudaMemcpyAsync(ranks_out, dout + o_ranks, G * P * 2, cudaMemcpyDeviceToHost, 0));
-    PHE_CUDA(cudaStreamSynchronize(0));
+    PHE_CUDA(cudaMemcpyAsync(winners_out, dout + o_win, G * 4, cudaMemcpyDeviceToHost, hs));
+    if (ranks_out) PHE_CUDA(cudaMemcpyAsync(ranks_out, dout + o_ranks, G * P * 2, cudaMemcpyDeviceToHost, hs));
+    PHE_CUDA(cudaStreamSynchronize(hs));
     return PHE_OK;
 }
 
@@ -1443,32 +1479,34 @@ int phe_settle_host(const uint64_t* boards, const uint64_t* holes, const int8_t*
     const size_t o_w = take(G * P * 4), o_r = take(G * P), o_c = take(G * P), o_p = take(G * 4);
     const size_t out_bytes = off;
     int rc;
+    cudaStream_t hs;
+    if ((rc = t_hstream.get(&hs))) return rc;
     if ((rc = t_in.ensure(in_bytes)) || (rc = t_out.ensure(out_bytes))) return rc;
     char* di = static_cast<char*>(t_in.p);
     char* dout = static_cast<char*>(t_out.p);
-    PHE_CUDA(cudaMemcpyAsync(di + o_b, boards, G * 8, cudaMemcpyHostToDevice, 0));
-    PHE_CUDA(cudaMemcpyAsync(di + o_h, holes, G * P * 8, cudaMemcpyHostToDevice, 0));
-    PHE_CUDA(cudaMemcpyAsync(di + o_a, actions, G * R * P, cudaMemcpyHostToDevice, 0));
-    PHE_CUDA(cudaMemcpyAsync(di + o_v, values, G * R * P * 4, cudaMemcpyHostToDevice, 0));
-    PHE_CUDA(cudaMemcpyAsync(di + o_n, n_rounds, G * 4, cudaMemcpyHostToDevice, 0));
-    PHE_CUDA(cudaMemcpyAsync(di + o_bt, button, G * 4, cudaMemcpyHostToDevice, 0));
-    PHE_CUDA(cudaMemcpyAsync(di + o_ob, onboard, G * 4, cudaMemcpyHostToDevice, 0));
+    PHE_CUDA(cudaMemcpyAsync(di + o_b, boards, G * 8, cudaMemcpyHostToDevice, hs));
+    PHE_CUDA(cudaMemcpyAsync(di + o_h, holes, G * P * 8, cudaMemcpyHostToDevice, hs));
+    PHE_CUDA(cudaMemcpyAsync(di + o_a, actions, G * R * P, cudaMemcpyHostToDevice, hs));
+    PHE_CUDA(cudaMemcpyAsync(di + o_v, values, G * R * P * 4, cudaMemcpyHostToDevice, hs));
+    PHE_CUDA(cudaMemcpyAsync(di + o_n, n_rounds, G * 4, cudaMemcpyHostToDevice, hs));
+    PHE_CUDA(cudaMemcpyAsync(di + o_bt, button, G * 4, cudaMemcpyHostToDevice, hs));
+    PHE_CUDA(cudaMemcpyAsync(di + o_ob, onboard, G * 4, cudaMemcpyHostToDevice, hs));
     if ((rc = phe_settle(reinterpret_cast<uint64_t*>(di + o_b), reinterpret_cast<uint64_t*>(di + o_h), reinterpret_cast<int8_t*>(di + o_a),
                          reinterpret_cast<int32_t*>(di + o_v), reinterpret_cast<int32_t*>(di + o_n), reinterpret_cast<int32_t*>(di + o_bt),
                          reinterpret_cast<uint32_t*>(di + o_ob), n_games, n_players, max_rounds, small_blind, reinterpret_cast<int32_t*>(dout + o_w),
-                         reinterpret_cast<int8_t*>(dout + o_r), reinterpret_cast<int8_t*>(dout + o_c), reinterpret_cast<uint32_t*>(dout + o_p), nullptr)))
+                         reinterpret_cast<int8_t*>(dout + o_r), reinterpret_cast<int8_t*>(dout + o_c), reinterpret_cast<uint32_t*>(dout + o_p), hs)))
         return rc;
-    PHE_CUDA(cudaMemcpyAsync(won_out, dout + o_w, G * P * 4, cudaMemcpyDeviceToHost, 0));
-    PHE_CUDA(cudaMemcpyAsync(result_out, dout + o_r, G * P, cudaMemcpyDeviceToHost, 0));
-    PHE_CUDA(cudaMemcpyAsync(card_result_out, dout + o_c, G * P, cudaMemcpyDeviceToHost, 0));
-    if (paid_out) PHE_CUDA(cudaMemcpyAsync(paid_out, dout + o_p, G * 4, cudaMemcpyDeviceToHost, 0));
-    PHE_CUDA(cudaStreamSynchronize(0));
+    PHE_CUDA(cudaMemcpyAsync(won_out, dout + o_w, G * P * 4, cudaMemcpyDeviceToHost, hs));
+    PHE_CUDA(cudaMemcpyAsync(result_out, dout + o_r, G * P, cudaMemcpyDeviceToHost, hs));
+    PHE_CUDA(cudaMemcpyAsync(card_result_out, dout + o_c, G * P, cudaMemcpyDeviceToHost, hs));
+    if (paid_out) PHE_CUDA(cudaMemcpyAsync(paid_out, dout + o_p, G * 4, cudaMemcpyDeviceToHost, hs));
+    PHE_CUDA(cudaStreamSynchronize(hs));
     return PHE_OK;
 }
 
 // ---- deal --------------------------------------------------------------------------------------
-int phe_deal(const uint64_t* known, int64_t n, int need, uint64_t seed, uint64_t sample_offset, uint32_t stream_base,
-             uint8_t* cards_out, void* stream)
+static int launch_deal(const uint64_t* known, int64_t n, int need, uint64_t seed, uint64_t sample_offset, uint32_t stream_base, int by_sample,
+                       uint8_t* cards_out, void* stream)
 {
     if (n < 0 || need < 1 || need > MAX_DEAL) return PHE_EINVAL;
     if (n == 0) return PHE_OK;
@@ -1477,24 +1515,46 @@ int phe_deal(const uint64_t* known, int64_t n, int need, uint64_t seed, uint64_t
     int rc = current_ctx(&cx);
     if (rc) return rc;
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    k_deal<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(cx->d_pairmask, known, n, need, seed, sample_offset, stream_base, cards_out);
+    k_deal<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(cx->d_pairmask, known, n, need, seed, sample_offset, stream_base, by_sample, cards_out);
     return after_launch("deal launch");
 }
 
-int phe_deal_host(const uint64_t* known, int64_t n, int need, uint64_t seed, uint64_t sample_offset, uint32_t stream_base,
-                  uint8_t* cards_out)
+static int deal_host(const uint64_t* known, int64_t n, int need, uint64_t seed, uint64_t sample_offset, uint32_t stream_base, int by_sample,
+                     uint8_t* cards_out)
 {
     if (n < 0 || need < 1 || need > MAX_DEAL) return PHE_EINVAL;
     if (n == 0) return PHE_OK;
     if (!known || !cards_out) return PHE_EINVAL;
     int rc;
+    cudaStream_t hs;
+    if ((rc = t_hstream.get(&hs))) return rc;
     if ((rc = t_in.ensure((size_t)n * 8)) || (rc = t_out.ensure((size_t)n * need))) return rc;
-    PHE_CUDA(cudaMemcpyAsync(t_in.p, known, (size_t)n * 8, cudaMemcpyHostToDevice, 0));
-    if ((rc = phe_deal(static_cast<const uint64_t*>(t_in.p), n, need, seed, sample_offset, stream_base, static_cast<uint8_t*>(t_out.p), nullptr)))
+    PHE_CUDA(cudaMemcpyAsync(t_in.p, known, (size_t)n * 8, cudaMemcpyHostToDevice, hs));
+    if ((rc = launch_deal(static_cast<const uint64_t*>(t_in.p), n, need, seed, sample_offset, stream_base, by_sample, static_cast<uint8_t*>(t_out.p), hs)))
         return rc;
-    PHE_CUDA(cudaMemcpyAsync(cards_out, t_out.p, (size_t)n * need, cudaMemcpyDeviceToHost, 0));
-    PHE_CUDA(cudaStreamSynchronize(0));
+    PHE_CUDA(cudaMemcpyAsync(cards_out, t_out.p, (size_t)n * need, cudaMemcpyDeviceToHost, hs));
+    PHE_CUDA(cudaStreamSynchronize(hs));
     return PHE_OK;
+}
+
+int phe_deal(const uint64_t* known, int64_t n, int need, uint64_t seed, uint64_t sample_offset, uint32_t stream_base, uint8_t* cards_out, void* stream)
+{
+    return launch_deal(known, n, need, seed, sample_offset, stream_base, 0, cards_out, stream);
+}
+
+int phe_deal_host(const uint64_t* known, int64_t n, int need, uint64_t seed, uint64_t sample_offset, uint32_t stream_base, uint8_t* cards_out)
+{
+    return deal_host(known, n, need, seed, sample_offset, stream_base, 0, cards_out);
+}
+
+int phe_deal_samples(const uint64_t* known, int64_t n, int need, uint64_t seed, uint64_t sample_offset, uint32_t stream_id, uint8_t* cards_out, void* stream)
+{
+    return launch_deal(known, n, need, seed, sample_offset, stream_id, 1, cards_out, stream);
+}
+
+int phe_deal_samples_host(const uint64_t* known, int64_t n, int need, uint64_t seed, uint64_t sample_offset, uint32_t stream_id, uint8_t* cards_out)
+{
+    return deal_host(known, n, need, seed, sample_offset, stream_id, 1, cards_out);
 }
 
 }  // extern "C"

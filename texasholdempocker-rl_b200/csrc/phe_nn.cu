@@ -380,14 +380,15 @@ k_attention(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict
                 }
             }
             // ---- softmax over the keys (rows g and g + 8 of the tile; a row lives in the four lanes of a quad) ----
-            // No masking: padded keys have K = 0, hence score 0 and probability exp2(-max * scale), and V = 0, so they
-            // add nothing to P V; their (112 - s_kv) equal terms are taken out of the row sum in closed form.  The
-            // running maximum therefore includes 0, which any valid softmax shift may.
-            float m0 = 0.f, m1 = 0.f;
+            // Padded key columns (index >= s_kv; K = V = 0) are masked out of both the row maximum and the row sum, so a
+            // row whose real logits are all strongly negative keeps its full precision (a closed-form correction of the
+            // padded terms cancels catastrophically there).  Column of s[nt][j]: nt * 8 + 2 t + (j & 1).
+            const int lim = s_kv - 2 * t;              // s[nt][0|2] is real iff nt * 8 < lim, s[nt][1|3] iff nt * 8 + 1 < lim
+            float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
             for (int nt = 0; nt < NT; nt++) {
-                m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
-                m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+                if (nt * 8 < lim) { m0 = fmaxf(m0, s[nt][0]); m1 = fmaxf(m1, s[nt][2]); }
+                if (nt * 8 + 1 < lim) { m0 = fmaxf(m0, s[nt][1]); m1 = fmaxf(m1, s[nt][3]); }
             }
             m0 = fmaxf(m0, __shfl_xor_sync(0xFFFFFFFFu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xFFFFFFFFu, m0, 2));
             m1 = fmaxf(m1, __shfl_xor_sync(0xFFFFFFFFu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xFFFFFFFFu, m1, 2));
@@ -396,8 +397,9 @@ k_attention(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict
             uint32_t p[NT][2];                       // probabilities as bf16 pairs: [nt][0] row g, [nt][1] row g + 8
 #pragma unroll
             for (int nt = 0; nt < NT; nt++) {
-                const float e0 = ex2(fmaf(s[nt][0], scale_log2e, -c0)), e1 = ex2(fmaf(s[nt][1], scale_log2e, -c0));
-                const float e2 = ex2(fmaf(s[nt][2], scale_log2e, -c1)), e3 = ex2(fmaf(s[nt][3], scale_log2e, -c1));
+                const bool ra = nt * 8 < lim, rb = nt * 8 + 1 < lim;
+                const float e0 = ra ? ex2(fmaf(s[nt][0], scale_log2e, -c0)) : 0.f, e1 = rb ? ex2(fmaf(s[nt][1], scale_log2e, -c0)) : 0.f;
+                const float e2 = ra ? ex2(fmaf(s[nt][2], scale_log2e, -c1)) : 0.f, e3 = rb ? ex2(fmaf(s[nt][3], scale_log2e, -c1)) : 0.f;
                 l0 += e0 + e1;
                 l1 += e2 + e3;
                 p[nt][0] = pack_bf16(e0, e1);
@@ -405,8 +407,7 @@ k_attention(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict
             }
             l0 += __shfl_xor_sync(0xFFFFFFFFu, l0, 1); l0 += __shfl_xor_sync(0xFFFFFFFFu, l0, 2);
             l1 += __shfl_xor_sync(0xFFFFFFFFu, l1, 1); l1 += __shfl_xor_sync(0xFFFFFFFFu, l1, 2);
-            const float npad = (float)(kAttnMaxKeys - s_kv);
-            const float inv0 = 1.f / (l0 - npad * ex2(-c0)), inv1 = 1.f / (l1 - npad * ex2(-c1));
+            const float inv0 = 1.f / l0, inv1 = 1.f / l1;             // >= 1: the row maximum is a real key
             // ---- O = P V: the score accumulators of key tiles (2j, 2j + 1) are exactly the A fragment of k-step j ----
             float o[DT][4];
 #pragma unroll

@@ -7,8 +7,10 @@
 // (ties in seat order); a seat whose action in a round is None still contends (the reference tests `!= FOLD`);
 // the game result is the one written by the last showdown a seat won; chips are floored to small-blind multiples
 // and the odd chips go to the button if it won, else to the next ONBOARD seat after the button if that won.
-// Where the reference's odd-chip loop would not terminate (env/game.py:731-733, more than two players) the chips
-// go to the first winner clockwise from the button.
+// Two deliberate fixes for tables of more than two seats, where the reference itself cannot finish: (1) where its
+// odd-chip loop would not terminate (env/game.py:731-733) the chips go to the first winner clockwise from the button;
+// (2) a final pot left without a contender (every seat still in the hand was settled as an all-in layer; the reference
+// divides by an empty winner set, env/game.py:721) goes to the best hand among the seats that have not folded.
 #pragma once
 #include "phe_core.cuh"
 
@@ -48,7 +50,7 @@ PHE_HD void settle_pay(int64_t total, uint32_t winners, int32_t* won, uint32_t* 
     *paid |= winners;
     const int64_t left = total - share * n;
     if (left > 0) {
-        int who = button;
+        int who = button;   // callers pass a seat index in [0, P) (k_settle reduces it)
         if (!(winners >> who & 1)) {
             int q = -1;
             for (int k = 1; k < P && q < 0; k++) {
@@ -125,6 +127,9 @@ PHE_HD void settle_game(int P, int R, int button, int small_blind, uint32_t onbo
         uint32_t cont = 0;
         for (int p = 0; p < P; p++)
             if (a[p] != ACT_FOLD && !(all_shared >> p & 1)) cont |= 1u << p;
+        if (!cont)   // every seat still in the hand was settled as an all-in layer: the reference divides by zero (env/game.py:721)
+            for (int p = 0; p < P; p++)
+                if (a[p] != ACT_FOLD) cont |= 1u << p;
         const uint32_t w = settle_winners(ranks, cont, P);
         settle_mark(w, result, P);
         settle_pay(pot, w, won, paid, small_blind, button, onboard, P);

@@ -186,21 +186,25 @@ def showdown(boards, holes, live=None, return_ranks=False):
     return (win, ranks) if return_ranks else win
 
 
-def deal(known, need, seed, sample_offset=0, stream_base=0):
-    """known int64[B] card sets -> uint8[B,need] ids drawn uniformly without replacement from the rest."""
+def deal(known, need, seed, sample_offset=0, stream_base=0, by_sample=False):
+    """known int64[B] card sets -> uint8[B,need] ids drawn uniformly without replacement from the rest.
+
+    Row i draws (stream stream_base + i, sample sample_offset) -- or, with by_sample=True, (stream stream_base,
+    sample sample_offset + i): n re-deals of ONE logical stream (phe_deal_samples)."""
     L = N.lib()
+    dev_fn, host_fn = (L.phe_deal_samples, L.phe_deal_samples_host) if by_sample else (L.phe_deal, L.phe_deal_host)
     if _is_cuda_tensor(known):
         k = known.contiguous()
         out = torch.empty(k.shape[0], need, dtype=torch.uint8, device=k.device)
         with torch.cuda.device(k.device):
             _use_device(k.device.index)
-            N.check(L.phe_deal(C.c_void_p(k.data_ptr()), k.shape[0], int(need), int(seed) & (2**64 - 1), int(sample_offset), int(stream_base),
-                               C.c_void_p(out.data_ptr()), _stream_ptr()))
+            N.check(dev_fn(C.c_void_p(k.data_ptr()), k.shape[0], int(need), int(seed) & (2**64 - 1), int(sample_offset), int(stream_base),
+                           C.c_void_p(out.data_ptr()), _stream_ptr()))
         return out
     k = np.ascontiguousarray(known, dtype=np.int64)
     out = np.zeros((k.shape[0], need), dtype=np.uint8)
     _use_device(_current_device())
-    N.check(L.phe_deal_host(_np_ptr(k), k.shape[0], int(need), int(seed) & (2**64 - 1), int(sample_offset), int(stream_base), _np_ptr(out)))
+    N.check(host_fn(_np_ptr(k), k.shape[0], int(need), int(seed) & (2**64 - 1), int(sample_offset), int(stream_base), _np_ptr(out)))
     return out
 
 
@@ -216,8 +220,9 @@ def determinise(hero_cards, board_cards, n_players, n, seed, sample_offset=0, st
 
     hero_cards: the acting player's two cards; board_cards: the revealed board (0, 3, 4 or 5 cards); n_players: seats
     at the table.  Returns (opp_holes uint8[n, n_players-1, 2] with each hand sorted as the reference sorts it,
-    board uint8[n, 5] = revealed cards followed by the newly dealt ones, the dealt flop part sorted).  Re-deal i uses
-    sample index sample_offset + i of stream `stream`; results are numpy arrays (host).
+    board uint8[n, 5] = revealed cards followed by the newly dealt ones, the dealt flop part sorted).  Re-deal i is
+    sample (sample_offset + i) of Philox stream `stream` (phe_deal_samples): a caller that numbers its games / trees with
+    `stream` never sees the same deal under two of them; results are numpy arrays (host).
     """
     hero = [card_id(c) for c in hero_cards]
     shown = [card_id(c) for c in (board_cards or [])]
@@ -229,9 +234,7 @@ def determinise(hero_cards, board_cards, n_players, n, seed, sample_offset=0, st
     if not 1 <= n_opp <= 8 or need > 21:
         raise ValueError("1..8 opponents")
     known = np.full(int(n), cards_to_mask(hero + shown), dtype=np.int64)
-    # one deal per re-deal: stream id fixed, sample index = re-deal number -> phe_deal's per-row stream is its row index,
-    # so rows are made distinct through stream_base = stream and sample_offset; each row i uses stream (stream + i).
-    ids = deal(known, need, seed, sample_offset=sample_offset, stream_base=stream)
+    ids = deal(known, need, seed, sample_offset=sample_offset, stream_base=stream, by_sample=True)
     odd = need & 1
     # slot order of phe_deal: [single if need is odd][pairs ...]; opponents take the first pairs, the board the rest
     opp = np.sort(ids[:, odd:odd + 2 * n_opp].reshape(n, n_opp, 2), axis=2)

@@ -215,19 +215,28 @@ class PolicyValueNet(nn.Module):
     def load_reference_state_dict(self, state_dict):
         """Accepts the state_dict of the reference model or of its ``AlphaGoZero`` wrapper (keys prefixed ``model.``)."""
         sd = {(k[6:] if k.startswith("model.") else k): v for k, v in state_dict.items()}
-        res = self.load_state_dict(sd, strict=True)
-        self._folded = None
-        return res
+        return self.load_state_dict(sd, strict=True)        # in place; _fold() notices the new tensor versions
 
     def _fold(self):
-        """Constants of the input embedding: scaled position half of every token and the scaled starter tokens."""
+        """Inference-time tables: position half of every token, the five starter tokens and the sqrt(d) scaling folded
+        together.  They live in PERSISTENT buffers: when the weights change in place (load_state_dict, an optimiser step)
+        the tables are recomputed into the same storage, so CUDA graphs that captured their addresses stay valid; the
+        buffers are only re-allocated when the weights move to another device or dtype (BatchedPredictor re-captures then)."""
         w = self.env_embedding.field_embedding.weight
-        key = (w.device, w.dtype, w._version, self.env_embedding.position_embedding.weight._version)
-        if self._folded is None or self._folded[0] != key:
-            pos = (self.env_embedding.position_embedding.weight * self.scale).to(w.dtype)            # [S, dp]
-            starters = torch.cat([w[:NUM_STARTERS] * self.scale, pos[:NUM_STARTERS]], dim=1)       # [5, d]
-            self._folded = (key, pos[NUM_STARTERS:].contiguous(), starters.contiguous(), (w * self.scale).contiguous())
-        return self._folded[1:]
+        pw = self.env_embedding.position_embedding.weight
+        place, version = (w.device, w.dtype), (w._version, pw._version, w.data_ptr(), pw.data_ptr())
+        if self._folded is not None and self._folded[0] == place and self._folded[1] == version:
+            return self._folded[2:]
+        with torch.no_grad():
+            pos = (pw * self.scale).to(w.dtype)                                                       # [S, dp]
+            fresh = (pos[NUM_STARTERS:], torch.cat([w[:NUM_STARTERS] * self.scale, pos[:NUM_STARTERS]], dim=1), w * self.scale)
+            if self._folded is not None and self._folded[0] == place:
+                for buf, val in zip(self._folded[2:], fresh):
+                    buf.copy_(val)
+                self._folded = (place, version) + self._folded[2:]
+            else:
+                self._folded = (place, version) + tuple(t.contiguous().clone() for t in fresh)
+        return self._folded[2:]
 
     # -- forward ---------------------------------------------------------------------------------------------------
     def embed(self, x):
@@ -333,6 +342,7 @@ class BatchedPredictor:
         self.max_batch = self.buckets[-1]
         self._lock = threading.Lock()
         self._graphs = {}
+        self._fold_token = None
         self._stream = torch.cuda.Stream(device=self.device)
         self._pin_in = torch.empty((self.max_batch, self.n_fields), dtype=torch.int32).pin_memory()
         self._pin_out = torch.empty((self.max_batch, self.n_actions + 1), dtype=torch.float32).pin_memory()
@@ -367,8 +377,29 @@ class BatchedPredictor:
             g = self._graphs[b] = (graph, x, out)
         return g
 
+    def _refresh_tables(self):
+        """Called on the predictor's stream before every replay: refolds the embedding tables if the weights changed in
+        place (same storage: the captured graphs stay valid) and drops the graphs if the tables were re-allocated."""
+        token = tuple(t.data_ptr() for t in self.model._fold())
+        if token != self._fold_token:
+            self._graphs.clear()
+            self._fold_token = token
+
+    def load_reference_state_dict(self, state_dict):
+        """Weight update of a live predictor (the reference's predict_batch_process reloads checkpoints through
+        update_model_param_queue, env/workflow.py:274-593): parameters are overwritten IN PLACE on the predictor's stream,
+        the folded tables follow in place, and the captured graphs keep replaying with the new weights."""
+        with self._lock, torch.cuda.stream(self._stream), torch.no_grad():
+            res = self.model.load_reference_state_dict(state_dict)
+            self._refresh_tables()
+            self._stream.synchronize()
+        return res
+
+    update_weights = load_reference_state_dict
+
     def warmup(self):
-        with self._lock:
+        with self._lock, torch.cuda.stream(self._stream):
+            self._refresh_tables()
             for b in self.buckets:
                 self._graph(b)
         torch.cuda.synchronize(self.device)
@@ -390,6 +421,7 @@ class BatchedPredictor:
         with self._lock, torch.cuda.stream(self._stream):
             if on_device:
                 self._stream.wait_stream(caller)
+            self._refresh_tables()
             for lo in range(0, B, self.max_batch):
                 n = min(self.max_batch, B - lo)
                 graph, x, out = self._graph(self._bucket(n))
@@ -442,6 +474,4 @@ def fill_parameters(module, seed, std=0.05):
             if ".norm" in k and k.endswith("weight"):
                 r += 1.0
             v.copy_(r.to(v.dtype))
-    if hasattr(module, "_folded"):
-        module._folded = None
     return module

@@ -29,7 +29,11 @@ def settle(boards, holes, actions, values, n_rounds, button, onboard, small_blin
         b, h, a, v = boards.contiguous(), holes.contiguous(), actions.contiguous(), values.contiguous()
         nr, bt, ob = n_rounds.contiguous(), button.contiguous(), onboard.contiguous()
         G, P = h.shape
-        R = a.shape[1]
+        R = a.shape[1] if a.dim() == 3 else -1
+        if (a.shape != (G, R, P) or v.shape != (G, R, P) or not 1 <= R <= MAX_ROUNDS or b.shape != (G,) or nr.shape != (G,) or bt.shape != (G,)
+                or ob.shape != (G,) or (b.dtype, h.dtype, a.dtype, v.dtype, nr.dtype, bt.dtype) !=
+                (torch.int64, torch.int64, torch.int8, torch.int32, torch.int32, torch.int32) or ob.dtype not in (torch.int32, torch.uint32)):
+            raise ValueError("boards int64[G], holes int64[G,P], actions int8[G,R<=4,P], values int32[G,R,P], n_rounds / button / onboard int32[G]")
         dev = b.device
         won = torch.empty(G, P, dtype=torch.int32, device=dev)
         res = torch.empty(G, P, dtype=torch.int8, device=dev)
@@ -48,13 +52,17 @@ def settle(boards, holes, actions, values, n_rounds, button, onboard, small_blin
     bt = np.ascontiguousarray(button, dtype=np.int32)
     ob = np.ascontiguousarray(onboard, dtype=np.uint32)
     G, P = h.shape
-    R = a.shape[1]
-    if a.shape != (G, R, P) or v.shape != (G, R, P) or R > MAX_ROUNDS:
+    if a.ndim != 3 or a.shape != (G, a.shape[1], P) or v.shape != a.shape or not 1 <= a.shape[1] <= MAX_ROUNDS:
         raise ValueError("actions / values must be [G, R<=4, P]")
+    if b.shape != (G,) or nr.shape != (G,) or bt.shape != (G,) or ob.shape != (G,):
+        raise ValueError("boards, n_rounds, button, onboard must be [G]")
+    if G and (bt.min() < 0 or bt.max() >= P or nr.min() < 0 or nr.max() > a.shape[1]):
+        raise ValueError("button must be a seat index in [0, P) and n_rounds within [0, R]")
     won = np.zeros((G, P), dtype=np.int32)
     res = np.zeros((G, P), dtype=np.int8)
     card = np.zeros((G, P), dtype=np.int8)
     paid = np.zeros(G, dtype=np.uint32)
+    R = a.shape[1]
     _use_device(_current_device())
     N.check(L.phe_settle_host(*(_np_ptr(t) for t in (b, h, a, v, nr, bt, ob)), G, P, R, int(small_blind),
                               *(_np_ptr(t) for t in (won, res, card, paid))))
