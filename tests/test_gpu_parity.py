@@ -471,8 +471,11 @@ def test_host_calls_do_not_wait_for_other_streams(phe, oracle, torch):
     ids = rand_hands(64, 21)
     want = oracle.rank7_batch(ids)
     st = phe.pack_states([["As", "Ah"]], [["2c", "7d", "Tc"]])
-    phe.evaluate_cards(*ids[0].tolist())
+    board_and_hands = (["2c", "7d", "Tc"], ["3h"], ["9s"], {"a": ["As", "Ah"], "b": ["Kd", "Kc"]})
+    phe.evaluate_cards(*ids[0].tolist())            # first launches load their kernels lazily, which waits for running work: warm up
+    phe.eval7(ids)
     phe.equity_mc(st, 1, 2000, seed=5)
+    phe.GameEnv.get_winner_set_v2(*board_and_hands)
     torch.cuda.synchronize()
     done = torch.cuda.Event()
     torch.cuda._sleep(int(0.4 * 1.9e9))                 # ~0.4 s spin kernel on the default stream (one thread: leaves the SMs free)
@@ -482,7 +485,7 @@ def test_host_calls_do_not_wait_for_other_streams(phe, oracle, torch):
         assert phe.evaluate_cards(*ids[k].tolist()) == int(want[k])
     assert (phe.eval7(ids) == want).all()
     got = phe.equity_mc(st, 1, 2000, seed=5)
-    winners = phe.GameEnv.get_winner_set_v2(["2c", "7d", "Tc"], ["3h"], ["9s"], {"a": ["As", "Ah"], "b": ["Kd", "Kc"]})
+    winners = phe.GameEnv.get_winner_set_v2(*board_and_hands)
     dt = time.perf_counter() - t0
     still_running = not done.query()
     torch.cuda.synchronize()

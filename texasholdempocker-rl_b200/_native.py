@@ -35,7 +35,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    path = os.environ.get("PHE_B200_LIB") or _build.LIB        # the override selects an experiment build (tools/lab/mc_variants.py)
     if not os.path.exists(path):
         # built artefacts are not in git; build in-tree when a compiler is present, else fail loudly
         try:

@@ -39,12 +39,16 @@ def nvcc_path():
     return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, extra_flags=(), out=None):
+    """`extra_flags` / `out` build an experiment variant next to the product library (tools/lab/mc_variants.py)."""
     os.makedirs(LIBDIR, exist_ok=True)
-    if force or _stale(LIB, _all_deps()):
-        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + _sources(["phe_kernels.cu", "phe_nn.cu", "phe_obs.cu", "phe_tables.cpp"])
+    target = out or LIB
+    os.makedirs(os.path.dirname(target), exist_ok=True)
+    if force or _stale(target, _all_deps()):
+        cmd = ([nvcc_path()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] +
+               _sources(["phe_kernels.cu", "phe_nn.cu", "phe_obs.cu", "phe_tables.cpp"]))
         subprocess.check_call(cmd)
-    return LIB
+    return target
 
 
 def build_hostcheck(force=False):

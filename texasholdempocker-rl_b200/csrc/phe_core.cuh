@@ -39,7 +39,7 @@ constexpr uint32_t TAB_BYTES = TAB_U16 * 2;
 // multipliers of the two hash functions (found by the table builder, verified collision free).  `two` is the constant 2,
 // kept where the compiler cannot see it: table byte addresses are formed as idx * two + base, one IMAD on the FMA pipe
 // instead of a LEA / IADD3 on the logic pipe that bounds these kernels.
-struct HashParams { uint32_t a1, b1, a2, b2, two; };
+struct HashParams { uint32_t a1, b1, a2, b2, two, one; };   // `one` = 1, opaque like `two`: see or_disjoint
 // Range reductions are multiply-high (umulhi(h, n), Lemire) so that they run on the FMA pipe: the kernels are bound by
 // the logic (alu) pipe.  Ranges that are not powers of two keep the compiler from turning them back into shifts.
 constexpr uint32_t HASH_BUCKETS = 8191;        // bucket = umulhi(h1, 8191) in [0, 8191)
@@ -63,6 +63,32 @@ PHE_HD uint32_t umulhi32(uint32_t a, uint32_t b)
     return __umulhi(a, b);
 #else
     return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+// a | b for words WITHOUT common bits.  With -DPHE_PIPE_BALANCE it becomes one multiply-add on the FMA pipe (b * one + a,
+// `one` = HashParams::one, the constant 1 read from constant memory so that the compiler cannot fold it back) instead of a
+// LOP3 on the logic pipe.  Measured on the B200 (tools/lab/mc_variants.py, profiles/mc_variants_r02.jsonl): a LOSS in the
+// Monte-Carlo kernel (3.65e10 against 3.77e10 rollouts/s) -- the dealing loop is a dependent chain through `used`, and the
+// IMAD's latency costs more than the logic-pipe slot it frees -- so it is off by default and kept for the record.
+PHE_HD uint32_t or_disjoint(uint32_t a, uint32_t b, uint32_t one)
+{
+#if defined(__CUDA_ARCH__) && defined(PHE_PIPE_BALANCE)
+    return b * one + a;
+#else
+    (void)one;
+    return a | b;
+#endif
+}
+
+// a + b as b * one + a: the same trick for a plain addition (cursor bookkeeping of the dealing loop)
+PHE_HD uint32_t add_fma(uint32_t a, uint32_t b, uint32_t one)
+{
+#if defined(__CUDA_ARCH__) && defined(PHE_PIPE_BALANCE)
+    return b * one + a;
+#else
+    (void)one;
+    return a + b;
 #endif
 }
 
@@ -143,10 +169,10 @@ PHE_HD uint32_t maj3(uint32_t p, uint32_t q, uint32_t r)
 // ---- 7-card evaluator on a card-set word -----------------------------------------------------
 // m must have exactly 7 card bits set.  Branch free: the flush and the non-flush index are both
 // formed and one of them selects the single final table read.
+// perfect-hash slot of the rank multiset of the card set (lo, hi): the non-flush index
 template <class Tab>
-PHE_HD uint32_t eval7(uint64_t m, const Tab& tab, const HashParams& hp)
+PHE_HD uint32_t noflush_slot(uint32_t lo, uint32_t hi, const Tab& tab, const HashParams& hp)
 {
-    const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);   // lanes {D,C} and {S,H}
     // rank multiplicities, bit sliced: count(r) = b0 + 2*b1 + 4*b2
     const uint32_t x = lo ^ hi, a = lo & hi;
     const uint32_t x1 = x >> 16, a1 = a >> 16;
@@ -158,7 +184,14 @@ PHE_HD uint32_t eval7(uint64_t m, const Tab& tab, const HashParams& hp)
     const uint32_t h1 = key * hp.a1 + b2 * hp.b1;
     const uint32_t h2 = key * hp.a2 + b2 * hp.b2;
     const uint32_t d = tab.ld_disp(umulhi32(h1, HASH_BUCKETS), hp);
-    const uint32_t inf = (h2 + d * HASH_DISP_MUL) >> 16;
+    return (h2 + d * HASH_DISP_MUL) >> 16;
+}
+
+template <class Tab>
+PHE_HD uint32_t eval7(uint64_t m, const Tab& tab, const HashParams& hp)
+{
+    const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);   // lanes {D,C} and {S,H}
+    const uint32_t inf = noflush_slot(lo, hi, tab, hp);
     // flush: with 7 cards at most one suit lane holds >= 5
     const int plo = popc32(lo);
     const uint32_t w = plo >= 5 ? lo : hi;
@@ -167,6 +200,40 @@ PHE_HD uint32_t eval7(uint64_t m, const Tab& tab, const HashParams& hp)
     const uint32_t lane = pl >= 5 ? wl : (w >> 16);
     const bool fl = (pl >= 5) | (pw - pl >= 5);
     return tab.ld_rank(fl, lane, inf, hp);
+}
+
+// ---- several hands on ONE board (a Monte-Carlo rollout, a showdown) ---------------------------------------------------
+// A flush needs three board cards of its suit, and five board cards hold at most one such suit: it is found once per
+// board; per hand the test is then "board bits of that suit | the hand's bits of that suit has >= 5 bits" -- select,
+// shift, and-or, one POPC -- instead of the three POPCs and the selects of the general form.
+struct BoardFlush {
+    uint32_t lane;   // the board's rank bits in the candidate suit (0 if no suit holds three)
+    uint32_t sh;     // 0 / 16: position of that suit lane in its word
+    uint32_t pm;     // 0xFFFF if a candidate suit exists, else 0 (no hand can make a flush)
+    bool hi;         // candidate suit lives in the high word
+};
+
+PHE_HD BoardFlush board_flush(uint32_t blo, uint32_t bhi)
+{
+    const int c0 = popc32(blo & 0xFFFFu), c1 = popc32(blo) - c0, c2 = popc32(bhi & 0xFFFFu), c3 = popc32(bhi) - c2;
+    BoardFlush f;
+    f.hi = (c2 >= 3) | (c3 >= 3);
+    const bool up = f.hi ? (c3 >= 3) : (c1 >= 3);
+    const bool any = f.hi | (c0 >= 3) | (c1 >= 3);
+    f.sh = up ? 16u : 0u;
+    f.pm = any ? 0xFFFFu : 0u;
+    f.lane = ((f.hi ? bhi : blo) >> f.sh) & f.pm;
+    return f;
+}
+
+// rank of board (5 cards: blo, bhi) + hole (2 cards, disjoint from the board)
+template <class Tab>
+PHE_HD uint32_t eval7_board(uint32_t blo, uint32_t bhi, const BoardFlush& bf, uint64_t hole, const Tab& tab, const HashParams& hp)
+{
+    const uint32_t plo = (uint32_t)hole, phi = (uint32_t)(hole >> 32);
+    const uint32_t inf = noflush_slot(or_disjoint(blo, plo, hp.one), or_disjoint(bhi, phi, hp.one), tab, hp);
+    const uint32_t lane = (((bf.hi ? phi : plo) >> bf.sh) & bf.pm) | bf.lane;
+    return tab.ld_rank(popc32(lane) >= 5, lane, inf, hp);
 }
 
 PHE_HD int category_of(uint32_t rank)
@@ -226,7 +293,7 @@ struct GlobalDealTab {          // host / small kernels
 
 struct LocalSlots {             // host / small kernels: accepted slots kept in thread-local storage
     uint64_t single;
-    uint64_t pair[MAX_PAIR_SLOTS];
+    uint64_t pair[MAX_PAIR_SLOTS + 1];      // one spare row: see deal_slots
     PHE_HD void put_single(uint64_t m) { single = m; }
     PHE_HD void put_pair(int k, uint32_t, uint64_t m) { pair[k] = m; }
     PHE_HD uint64_t get_single() const { return single; }
@@ -235,7 +302,7 @@ struct LocalSlots {             // host / small kernels: accepted slots kept in 
     // cursor over the pair slots: an index here, a shared-memory address in the kernels' slot store
     typedef int cursor;
     PHE_HD cursor cursor_at(int k) const { return k; }
-    PHE_HD cursor cursor_next(cursor c) const { return c + 1; }
+    PHE_HD cursor cursor_next(cursor c, uint32_t) const { return c + 1; }
     PHE_HD int cursor_index(cursor c) const { return c; }
     PHE_HD void put_at(cursor c, uint32_t q, uint64_t m) { put_pair(c, q, m); }
 };
@@ -243,9 +310,9 @@ struct LocalSlots {             // host / small kernels: accepted slots kept in 
 // returns the number of pair slots accepted (== n_pairs unless the input was malformed)
 template <class DealTab, class Slots>
 PHE_HD int deal_slots(const DealTab& dt, uint64_t known, uint64_t seed, uint64_t sample, uint32_t stream, bool want_single, int n_pairs,
-                      Slots& out)
+                      Slots& out, uint32_t one = 1u)
 {
-    uint64_t used = known;
+    uint32_t used_lo = (uint32_t)known, used_hi = (uint32_t)(known >> 32);
     const uint32_t s_lo = (uint32_t)sample, s_hi = (uint32_t)(sample >> 32), k_lo = (uint32_t)seed, k_hi = (uint32_t)(seed >> 32);
     uint32_t rnd[4];
     philox4x32_10(s_lo, s_hi, stream, 0u, k_lo, k_hi, rnd);
@@ -255,7 +322,9 @@ PHE_UNROLL
         for (int h = 0; h < 2; h++) {
             const uint32_t r = (rnd[0] >> (16 * h)) & 0xFFFFu;
             const uint64_t m = dt.mask(N_PAIRS + mod52_u16(r));
-            if (!have && r < DEAL_SINGLE_LIMIT && !(m & used)) { have = true; used |= m; out.put_single(m); }
+            if (!have && r < DEAL_SINGLE_LIMIT && !(((uint32_t)m & used_lo) | ((uint32_t)(m >> 32) & used_hi))) {
+                have = true; used_lo |= (uint32_t)m; used_hi |= (uint32_t)(m >> 32); out.put_single(m);
+            }
         }
         for (uint32_t t = 0; !have && t < 64u; t++) {      // rare overflow path
             uint32_t ex[4];
@@ -263,12 +332,17 @@ PHE_UNROLL
             for (int d = 0; d < 8 && !have; d++) {
                 const uint32_t r = (ex[d >> 1] >> (16 * (d & 1))) & 0xFFFFu;
                 const uint64_t m = dt.mask(N_PAIRS + mod52_u16(r));
-                if (r < DEAL_SINGLE_LIMIT && !(m & used)) { have = true; used |= m; out.put_single(m); }
+                if (r < DEAL_SINGLE_LIMIT && !(((uint32_t)m & used_lo) | ((uint32_t)(m >> 32) & used_hi))) {
+                    have = true; used_lo |= (uint32_t)m; used_hi |= (uint32_t)(m >> 32); out.put_single(m);
+                }
             }
         }
     }
     // the number of accepted pairs is kept as a cursor into the slot store (an address in the kernels): the accept path
-    // is one store and one add, with no index-to-address multiply
+    // is one store and one add, with no index-to-address multiply.  The accept test does not look at the cursor: the word
+    // loop below stops as soon as the slots are full, so at most ONE further pair (second half of the last word) can be
+    // accepted after that -- it lands in the spare row n_pairs of the slot store and is never read.  The marks of an
+    // accepted pair are added, not OR-ed (its cards are free, no bit is shared): a multiply-add on the FMA pipe.
     typename Slots::cursor cur = out.cursor_at(0);
     const typename Slots::cursor end = out.cursor_at(n_pairs);
     int first_word = want_single ? 1 : 0;
@@ -284,17 +358,19 @@ PHE_UNROLL
                 const uint32_t r = (rnd[wi] >> (16 * h)) & 0xFFFFu;
                 const uint32_t q = mod1326_u16(r);
                 const uint64_t m = dt.mask(q);
-                if (r < DEAL_PAIR_LIMIT && !(m & used) && cur < end) {
-                    used |= m;
+                const uint32_t m_lo = (uint32_t)m, m_hi = (uint32_t)(m >> 32);
+                if (r < DEAL_PAIR_LIMIT && !((m_lo & used_lo) | (m_hi & used_hi))) {
+                    used_lo = or_disjoint(used_lo, m_lo, one);
+                    used_hi = or_disjoint(used_hi, m_hi, one);
                     out.put_at(cur, q, m);
-                    cur = out.cursor_next(cur);
+                    cur = out.cursor_next(cur, one);
                 }
             }
         }
         first_word = 0;
     }
     const int got = out.cursor_index(cur);
-    return got;
+    return got < n_pairs ? got : n_pairs;
 }
 
 // one Monte-Carlo rollout (env/workflow.py:130-148 generalised to n_opp opponents):
@@ -304,16 +380,27 @@ PHE_HD int mc_rollout(const Tab& tab, const HashParams& hp, const DealTab& dt, u
                       uint64_t seed, uint64_t sample, uint32_t stream, Slots& slots)
 {
     const int nbm = 5 - nboard, nbp = nbm >> 1;
-    deal_slots(dt, known, seed, sample, stream, (nbm & 1) != 0, nbp + n_opp, slots);
+    deal_slots(dt, known, seed, sample, stream, (nbm & 1) != 0, nbp + n_opp, slots, hp.one);
     uint64_t board = known & ~hero;
     if (nbm & 1) board |= slots.get_single();
     for (int k = 0; k < nbp; k++) board |= slots.get_pair(k, dt);
+    const uint32_t blo = (uint32_t)board, bhi = (uint32_t)(board >> 32);
+#ifndef PHE_MC_GENERIC_EVAL
+    const BoardFlush bf = board_flush(blo, bhi);        // the board is common to all n_opp + 1 hands of the rollout
+    const uint32_t hr = eval7_board(blo, bhi, bf, hero, tab, hp);
+    uint32_t best = 0xFFFFu;
+    for (int o = 0; o < n_opp; o++) {
+        const uint32_t r = eval7_board(blo, bhi, bf, slots.get_pair(nbp + o, dt), tab, hp);
+        best = r < best ? r : best;
+    }
+#else
     const uint32_t hr = eval7(board | hero, tab, hp);
     uint32_t best = 0xFFFFu;
     for (int o = 0; o < n_opp; o++) {
         const uint32_t r = eval7(board | slots.get_pair(nbp + o, dt), tab, hp);
         best = r < best ? r : best;
     }
+#endif
     return hr < best ? 0 : (hr == best ? 1 : 2);
 }
 
@@ -334,7 +421,7 @@ PHE_HD void deal_ids(const DealTab& dt, uint64_t known, uint64_t seed, uint64_t 
 {
     LocalSlots sl;
     sl.single = 0;
-    for (int k = 0; k < MAX_PAIR_SLOTS; k++) sl.pair[k] = 0;
+    for (int k = 0; k <= MAX_PAIR_SLOTS; k++) sl.pair[k] = 0;
     const int np = need >> 1, odd = need & 1;
     deal_slots(dt, known, seed, sample, stream, odd != 0, np, sl);
     if (odd) ids[0] = (uint8_t)pos_to_id(lowest_pos(sl.single));

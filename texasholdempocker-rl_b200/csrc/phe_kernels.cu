@@ -42,7 +42,17 @@ static constexpr uint32_t kSmemTabOnly = kSmemTab + 16;
 static constexpr uint32_t kSmemPairs = kSmemTabOnly + N_PAIRS * 8;
 static constexpr uint32_t kSmemEvalIds = kSmemTabOnly + (kCtaThreads / 32) * 896;      // + per-warp transpose strips of the id layout
 static constexpr uint32_t kDealTabBytes = DEALTAB_ENTRIES * 8;                 // 11,024
-static constexpr uint32_t kSmemMc = kSmemTabOnly + kDealTabBytes + MAX_PAIR_SLOTS * 4 * kCtaThreads;   // + deal table + slot scratch
+#ifndef PHE_MC_THREADS
+#define PHE_MC_THREADS 1024
+#endif
+#ifdef PHE_MC_CLUSTER1
+#define PHE_MC_CLUSTER_ATTR __cluster_dims__(1, 1, 1)
+#else
+#define PHE_MC_CLUSTER_ATTR
+#endif
+static constexpr int kMcThreads = PHE_MC_THREADS;                      // CTA size of k_equity_mc_smem (one CTA per SM)
+static constexpr uint32_t kMcSlotRows = MAX_PAIR_SLOTS + 1;            // + the spare row of deal_slots
+static constexpr uint32_t kSmemMc = kSmemTabOnly + kDealTabBytes + kMcSlotRows * 4 * kMcThreads;   // + deal table + slot scratch
 
 // ------------------------------------------------------------------------------------------------
 // table staging: one TMA bulk copy of the whole image, completion on an mbarrier
@@ -528,7 +538,7 @@ struct SmemSlots {
     }
     typedef uint32_t cursor;      // shared address of the next free cell of this thread's column
     __device__ __forceinline__ cursor cursor_at(int k) const { return base + (uint32_t)k * stride; }
-    __device__ __forceinline__ cursor cursor_next(cursor c) const { return c + stride; }
+    __device__ __forceinline__ cursor cursor_next(cursor c, uint32_t one) const { return add_fma(c, stride, one); }
     __device__ __forceinline__ int cursor_index(cursor c) const { return (int)((c - base) / stride); }
     __device__ __forceinline__ void put_at(cursor c, uint32_t q, uint64_t)
     {
@@ -588,7 +598,7 @@ __device__ __forceinline__ void equity_mc_body(const Tab& tab, const DealTab& dt
     }
 }
 
-__global__ void __launch_bounds__(kCtaThreads, 1)
+__global__ void __launch_bounds__(kMcThreads, 1) PHE_MC_CLUSTER_ATTR
 k_equity_mc_smem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict__ g_dealtab, const ulonglong2* __restrict__ states,
                  int64_t n_states, int n_opp, uint64_t rollouts, uint64_t sample_offset, uint64_t seed, uint32_t state_base,
                  unsigned long long* __restrict__ wtl, uint32_t chunk, unsigned int* __restrict__ counters)
@@ -598,11 +608,228 @@ k_equity_mc_smem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
     for (uint32_t i = threadIdx.x; i < DEALTAB_ENTRIES; i += blockDim.x) s_deal[i] = g_dealtab[i];
     stage_tables(smem, g_tab, reinterpret_cast<uint64_t*>(smem + kSmemTab));   // includes a __syncthreads
     __syncthreads();
-    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem);
+    uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem);
+#ifndef PHE_MC_REMAT_BASE
+    // always + 0, but opaque to ptxas: the shared-window base then stays in a register instead of being rebuilt
+    // (S2R CgaCtaId, MOV, VIADD, LEA) in front of every table access of the dealing loop
+    sb += (uint32_t)(rollouts >> 63);
+#endif
     const SharedTab tab{sb};
     const SharedDealTab dt{sb + kSmemTabOnly};
     const SmemSlots slots{sb + kSmemTabOnly + kDealTabBytes + 4u * threadIdx.x, 4u * blockDim.x, 0ull};
     equity_mc_body(tab, dt, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk, slots, counters);
+    // completion ticket: the last CTA re-arms the {item counter, ticket} pair for the next launch that draws it
+    __shared__ uint32_t s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(counters + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        counters[0] = 0;
+        counters[1] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 (round 2): Monte-Carlo equity with dealing decoupled from evaluation.
+//
+// In the kernel above a warp deals 32 samples in lock step and waits for its slowest lane: rejection sampling needs a
+// different number of draws per sample, so the dealing loop -- 60 % of the instructions -- ran at ~20 of 32 lanes (ncu:
+// 16 draw slots executed per rollout against 9.3 needed, 2.5 Philox blocks against 1.7).  Here every lane walks its OWN
+// sequence of samples (lane, lane + 32, ... of the item's chunk): one ROUND = one Philox block + its eight draws for
+// whatever sample the lane is working on, all 32 lanes busy.  A lane that completes a deal publishes the shared-memory
+// column holding its accepted slots on the warp's READY ring, takes a free column and starts its next sample in the
+// following round; whenever 32 deals are ready the warp evaluates them together, lane j taking the j-th ready column --
+// evaluation always runs on 32 lanes, whoever dealt the hands.  The deal of (state, sample) and therefore every count
+// is unchanged (same stream contract as deal_slots / the oracle).
+//
+// Per warp: 64 columns x 12 rows of u16 cells (rows 0..9 pair slots, row n_pairs doubles as the spare row of the
+// clamped cursor, row 11 the single card) = [row][64] so that any 32 distinct columns are bank-conflict free, plus a
+// 64-entry ring of column ids split into a free and a ready segment: 32 columns are always held by the lanes.
+// ------------------------------------------------------------------------------------------------
+static constexpr uint32_t kPoolRows = MAX_PAIR_SLOTS + 2;
+static constexpr uint32_t kPoolRowBytes = 128;                         // 64 columns x u16
+static constexpr uint32_t kPoolSingleRow = kPoolRows - 1;
+static constexpr uint32_t kPoolWarpBytes = kPoolRows * kPoolRowBytes + 64;   // + ring of 64 column ids (u8)
+static constexpr uint32_t kSmemMcPool = kSmemTabOnly + kDealTabBytes + (kCtaThreads / 32) * kPoolWarpBytes;
+static_assert(kSmemMcPool <= 232448, "Monte-Carlo pool kernel: shared memory budget");
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u16v(uint32_t a)
+{
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(kCtaThreads, 1)
+k_equity_mc_pool(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict__ g_dealtab, const ulonglong2* __restrict__ states,
+                 int64_t n_states, int n_opp_default, uint64_t rollouts, uint64_t sample_offset, uint64_t seed, uint32_t state_base,
+                 unsigned long long* __restrict__ wtl, uint32_t chunk, unsigned int* __restrict__ counters)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* s_deal = reinterpret_cast<uint64_t*>(smem + kSmemTabOnly);
+    for (uint32_t i = threadIdx.x; i < DEALTAB_ENTRIES; i += blockDim.x) s_deal[i] = g_dealtab[i];
+    stage_tables(smem, g_tab, reinterpret_cast<uint64_t*>(smem + kSmemTab));   // includes a __syncthreads
+    uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem);
+    sb += (uint32_t)(rollouts >> 63);        // + 0, opaque to ptxas: keeps the shared-window base in a register (see k_equity_mc_smem)
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t wcells = sb + kSmemTabOnly + kDealTabBytes + warp * kPoolWarpBytes;
+    const uint32_t ring = wcells + kPoolRows * kPoolRowBytes;
+    sts_u8(ring + lane, 32u + lane);         // free segment: columns 32..63; lane holds column `lane`
+    __syncthreads();
+    const HashParams hp = c_hp;
+    const SharedTab tab{sb};
+    const SharedDealTab dt{sb + kSmemTabOnly};
+    const uint32_t k_lo = (uint32_t)seed, k_hi = (uint32_t)(seed >> 32);
+    uint32_t col = lane;
+    uint32_t rf = 0, rr = 32, rt = 32;       // ring cursors: free [rf, rr), ready [rr, rt)  (mod 64)
+
+    const uint64_t chunks_per_state = (rollouts + chunk - 1) / chunk;
+    const uint64_t items = (uint64_t)n_states * chunks_per_state;
+    for (;;) {
+        uint32_t nxt = 0;
+        if (lane == 0) nxt = atomicAdd(counters, 1u);
+        const uint64_t item = __shfl_sync(0xFFFFFFFFu, nxt, 0);
+        if (item >= items) break;
+        const uint64_t s = item / chunks_per_state, ch = item - s * chunks_per_state;
+        const ulonglong2 st = states[s];
+        const uint64_t known = st.x & CARD_BITS, hero = st.y & CARD_BITS;
+        const int over = (int)(st.y >> 61);
+        const int n_opp = over ? over : n_opp_default;
+        const int nbm = 5 - __popcll(known & ~hero), nbp = nbm >> 1;
+        const bool want_single = (nbm & 1) != 0;
+        const uint32_t n_pairs = (uint32_t)(nbp + n_opp);
+        const uint64_t b = ch * chunk;
+        const uint32_t limit = (uint32_t)((b + chunk > rollouts ? rollouts : b + chunk) - b);
+        const uint64_t base_sample = sample_offset + b;
+        const uint32_t stream = state_base + (uint32_t)s;
+        const uint32_t known_lo = (uint32_t)known, known_hi = (uint32_t)(known >> 32);
+        const uint32_t kb_lo = (uint32_t)(known & ~hero), kb_hi = (uint32_t)((known & ~hero) >> 32);
+
+        // evaluation of n ready deals: lane j takes the j-th ready column
+        uint32_t acc = 0;                    // three 10-bit counters (win, tie, loss): a lane evaluates <= chunk / 32 + 1 <= 257 deals per item
+        auto evaluate = [&](uint32_t first, uint32_t n) {
+            if (lane < n) {
+                const uint32_t cb = wcells + 2u * lds_u8(ring + ((first + lane) & 63u));
+                uint32_t blo = kb_lo, bhi = kb_hi;
+                if (want_single) {
+                    const uint64_t m = dt.mask(lds_u16v(cb + kPoolSingleRow * kPoolRowBytes));
+                    blo |= (uint32_t)m; bhi |= (uint32_t)(m >> 32);
+                }
+                for (int k = 0; k < nbp; k++) {
+                    const uint64_t m = dt.mask(lds_u16v(cb + (uint32_t)k * kPoolRowBytes));
+                    blo |= (uint32_t)m; bhi |= (uint32_t)(m >> 32);
+                }
+                const BoardFlush bf = board_flush(blo, bhi);
+                const uint32_t hr = eval7_board(blo, bhi, bf, hero, tab, hp);
+                uint32_t best = 0xFFFFu;
+                for (int o = 0; o < n_opp; o++) {
+                    const uint32_t r = eval7_board(blo, bhi, bf, dt.mask(lds_u16v(cb + (uint32_t)(nbp + o) * kPoolRowBytes)), tab, hp);
+                    best = r < best ? r : best;
+                }
+                acc += hr < best ? 1u : (hr == best ? (1u << 10) : (1u << 20));
+            }
+            __syncwarp();
+        };
+
+        // per-lane dealing state
+        uint32_t rel = lane;                 // sample index within the item
+        bool live = rel < limit;
+        uint32_t blk = 0;
+        uint32_t used_lo = live ? known_lo : 0xFFFFFFFFu, used_hi = live ? known_hi : 0xFFFFFFFFu;   // all ones: nothing is ever accepted
+        uint32_t cur = wcells + 2u * col;
+        uint32_t end = cur + n_pairs * kPoolRowBytes;
+
+        while (__any_sync(0xFFFFFFFFu, live)) {
+            const uint64_t sample = base_sample + rel;
+            uint32_t rnd[4];
+            philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), stream, blk, k_lo, k_hi, rnd);
+            const bool first = blk == 0;
+            if (want_single && first && live) {
+                // the single card: draws 0 and 1 of block 0 are reserved for it; overflow blocks 0x80000000 + t in the ~1 % case
+                bool have = false;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t r = (rnd[0] >> (16 * h)) & 0xFFFFu;
+                    const uint32_t c = N_PAIRS + mod52_u16(r);
+                    const uint64_t m = dt.mask(c);
+                    if (!have && r < DEAL_SINGLE_LIMIT && !(((uint32_t)m & used_lo) | ((uint32_t)(m >> 32) & used_hi))) {
+                        have = true; used_lo |= (uint32_t)m; used_hi |= (uint32_t)(m >> 32);
+                        sts_u16(wcells + 2u * col + kPoolSingleRow * kPoolRowBytes, c);
+                    }
+                }
+                for (uint32_t t = 0; !have && t < 64u; t++) {
+                    uint32_t ex[4];
+                    philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), stream, 0x80000000u + t, k_lo, k_hi, ex);
+                    for (int d = 0; d < 8 && !have; d++) {
+                        const uint32_t r = (ex[d >> 1] >> (16 * (d & 1))) & 0xFFFFu;
+                        const uint32_t c = N_PAIRS + mod52_u16(r);
+                        const uint64_t m = dt.mask(c);
+                        if (r < DEAL_SINGLE_LIMIT && !(((uint32_t)m & used_lo) | ((uint32_t)(m >> 32) & used_hi))) {
+                            have = true; used_lo |= (uint32_t)m; used_hi |= (uint32_t)(m >> 32);
+                            sts_u16(wcells + 2u * col + kPoolSingleRow * kPoolRowBytes, c);
+                        }
+                    }
+                }
+            }
+            const bool skip01 = want_single && first;      // the reserved word of block 0
+#pragma unroll
+            for (int wi = 0; wi < 4; wi++) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t r = (rnd[wi] >> (16 * h)) & 0xFFFFu;
+                    const uint32_t q = mod1326_u16(r);
+                    const uint64_t m = dt.mask(q);
+                    const uint32_t m_lo = (uint32_t)m, m_hi = (uint32_t)(m >> 32);
+                    bool ok = r < DEAL_PAIR_LIMIT && !((m_lo & used_lo) | (m_hi & used_hi));
+                    if (wi == 0) ok = ok && !skip01;
+                    if (ok) {
+                        used_lo |= m_lo; used_hi |= m_hi;
+                        sts_u16(cur, q);
+                        cur = cur + kPoolRowBytes < end ? cur + kPoolRowBytes : end;     // full: later accepts of this round land in the spare row
+                    }
+                }
+            }
+            const bool done = live && (cur == end || blk == 63u);      // 64 blocks are never reached by a valid state; bounds garbage
+            const uint32_t dm = __ballot_sync(0xFFFFFFFFu, done);
+            blk++;
+            if (dm) {
+                const uint32_t rank = __popc(dm & lt_mask), cnt = __popc(dm);
+                if (done) sts_u8(ring + ((rt + rank) & 63u), col);
+                rt += cnt;
+                __syncwarp();
+                while (rt - rr >= 32u) { evaluate(rr, 32u); rr += 32u; }
+                if (done) {
+                    col = lds_u8(ring + ((rf + rank) & 63u));
+                    rel += 32u;
+                    live = rel < limit;
+                    blk = 0;
+                    used_lo = live ? known_lo : 0xFFFFFFFFu;
+                    used_hi = live ? known_hi : 0xFFFFFFFFu;
+                    cur = wcells + 2u * col;
+                    end = cur + n_pairs * kPoolRowBytes;
+                }
+                rf += cnt;
+                __syncwarp();
+            }
+        }
+        if (rt != rr) { evaluate(rr, rt - rr); rr = rt; }
+        const uint32_t w = __reduce_add_sync(0xFFFFFFFFu, acc & 1023u), t = __reduce_add_sync(0xFFFFFFFFu, (acc >> 10) & 1023u),
+                       l = __reduce_add_sync(0xFFFFFFFFu, acc >> 20);
+        if (lane == 0) {
+            if (w) atomicAdd(wtl + 3 * s + 0, (unsigned long long)w);
+            if (t) atomicAdd(wtl + 3 * s + 1, (unsigned long long)t);
+            if (l) atomicAdd(wtl + 3 * s + 2, (unsigned long long)l);
+        }
+    }
     // completion ticket: the last CTA re-arms the {item counter, ticket} pair for the next launch that draws it
     __shared__ uint32_t s_last;
     __syncthreads();
@@ -619,7 +846,7 @@ k_equity_mc_gmem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
                  int64_t n_states, int n_opp, uint64_t rollouts, uint64_t sample_offset, uint64_t seed, uint32_t state_base,
                  unsigned long long* __restrict__ wtl, uint32_t chunk)
 {
-    __shared__ uint32_t s_slots[MAX_PAIR_SLOTS * 256];
+    __shared__ uint32_t s_slots[kMcSlotRows * 256];
     const GlobalTab tab{g_tab};
     const GlobalDealTab dt{g_dealtab};
     const SmemSlots slots{(uint32_t)__cvta_generic_to_shared(s_slots) + 4u * threadIdx.x, 4u * blockDim.x, 0ull};
@@ -966,6 +1193,7 @@ void init_device(int device)
     chk(cudaFuncSetAttribute(k_eval7_smem<PHE_LAYOUT_MASKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr eval7 masks");
     chk(cudaFuncSetAttribute(k_enum7, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEnum), "attr enum7");
     chk(cudaFuncSetAttribute(k_equity_mc_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMc), "attr equity_mc");
+    chk(cudaFuncSetAttribute(k_equity_mc_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMcPool), "attr equity_mc_pool");
     chk(cudaFuncSetAttribute(k_equity_plan_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr equity_plan");
     chk(cudaFuncSetAttribute(k_showdown_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr showdown");
 }
@@ -1257,7 +1485,7 @@ int phe_equity_mc(const uint64_t* states, int64_t n_states, int n_opp, uint64_t 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // samples per warp item: aim at >= 4 items per resident warp, 32..8192, multiple of 32
     const double total = (double)n_states * (double)rollouts;
-    const uint64_t warps = (uint64_t)cx->sm_count * (kCtaThreads / 32);
+    const uint64_t warps = (uint64_t)cx->sm_count * (kMcThreads / 32);
     uint64_t chunk = (uint64_t)(total / (double)(warps * 4));
     chunk = (chunk + 31) & ~(uint64_t)31;
     if (chunk < 32) chunk = 32;
@@ -1272,10 +1500,14 @@ int phe_equity_mc(const uint64_t* states, int64_t n_states, int n_opp, uint64_t 
         if (blocks > (uint64_t)cx->sm_count * 8) blocks = (uint64_t)cx->sm_count * 8;
         k_equity_mc_gmem<<<(unsigned)blocks, 256, 0, st>>>(cx->d_image, cx->d_pairmask, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk);
     } else {
-        uint64_t ctas = (items + 31) / 32;
+        uint64_t ctas = (items + kMcThreads / 32 - 1) / (kMcThreads / 32);
         if (ctas > (uint64_t)cx->sm_count) ctas = cx->sm_count;
         unsigned int* counters = cx->d_counters + 2 * (cx->next_counter.fetch_add(1, std::memory_order_relaxed) % kCounterRing);
-        k_equity_mc_smem<<<(unsigned)ctas, kCtaThreads, kSmemMc, st>>>(cx->d_image, cx->d_pairmask, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk, counters);
+#ifdef PHE_MC_V1
+        k_equity_mc_smem<<<(unsigned)ctas, kMcThreads, kSmemMc, st>>>(cx->d_image, cx->d_pairmask, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk, counters);
+#else
+        k_equity_mc_pool<<<(unsigned)ctas, kCtaThreads, kSmemMcPool, st>>>(cx->d_image, cx->d_pairmask, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk, counters);
+#endif
     }
     return after_launch("equity_mc launch");
 }

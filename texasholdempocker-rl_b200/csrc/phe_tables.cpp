@@ -249,7 +249,7 @@ bool build_table_image(uint16_t* image, HashParams* hp_out)
             s = s * 6364136223846793005ull + 1442695040888963407ull;
             v[i] = (uint32_t)(s >> 32) | 1u;
         }
-        HashParams hp{v[0], v[1], v[2], v[3], 2u};
+        HashParams hp{v[0], v[1], v[2], v[3], 2u, 1u};
         if (try_build(keys, hp, image)) { *hp_out = hp; return true; }
     }
     return false;
