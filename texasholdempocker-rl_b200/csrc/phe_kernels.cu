@@ -714,6 +714,9 @@ k_equity_mc_pool(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
         const uint32_t known_lo = (uint32_t)known, known_hi = (uint32_t)(known >> 32);
         const uint32_t kb_lo = (uint32_t)(known & ~hero), kb_hi = (uint32_t)((known & ~hero) >> 32);
 
+        // river states: the board is complete, so its flush context and the hero's rank are the same for every rollout
+        BoardFlush bf_river = board_flush(kb_lo, kb_hi);
+        const uint32_t hr_river = nbm == 0 ? eval7_board(kb_lo, kb_hi, bf_river, hero, tab, hp) : 0u;
         // evaluation of n ready deals: lane j takes the j-th ready column
         uint32_t acc = 0;                    // three 10-bit counters (win, tie, loss): a lane evaluates <= chunk / 32 + 1 <= 257 deals per item
         auto evaluate = [&](uint32_t first, uint32_t n) {
@@ -728,8 +731,12 @@ k_equity_mc_pool(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
                     const uint64_t m = dt.mask(lds_u16v(cb + (uint32_t)k * kPoolRowBytes));
                     blo |= (uint32_t)m; bhi |= (uint32_t)(m >> 32);
                 }
-                const BoardFlush bf = board_flush(blo, bhi);
-                const uint32_t hr = eval7_board(blo, bhi, bf, hero, tab, hp);
+                BoardFlush bf = bf_river;
+                uint32_t hr = hr_river;
+                if (nbm != 0) {                          // uniform per item
+                    bf = board_flush(blo, bhi);
+                    hr = eval7_board(blo, bhi, bf, hero, tab, hp);
+                }
                 uint32_t best = 0xFFFFu;
                 for (int o = 0; o < n_opp; o++) {
                     const uint32_t r = eval7_board(blo, bhi, bf, dt.mask(lds_u16v(cb + (uint32_t)(nbp + o) * kPoolRowBytes)), tab, hp);
@@ -747,6 +754,9 @@ k_equity_mc_pool(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
         uint32_t used_lo = live ? known_lo : 0xFFFFFFFFu, used_hi = live ? known_hi : 0xFFFFFFFFu;   // all ones: nothing is ever accepted
         uint32_t cur = wcells + 2u * col;
         uint32_t end = cur + n_pairs * kPoolRowBytes;
+#ifdef PHE_POOL_SKIP_READS
+        if (!live) cur = end;
+#endif
 
         while (__any_sync(0xFFFFFFFFu, live)) {
             const uint64_t sample = base_sample + rel;
@@ -787,6 +797,7 @@ k_equity_mc_pool(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
                 for (int h = 0; h < 2; h++) {
                     const uint32_t r = (rnd[wi] >> (16 * h)) & 0xFFFFu;
                     const uint32_t q = mod1326_u16(r);
+#ifndef PHE_POOL_SKIP_READS
                     const uint64_t m = dt.mask(q);
                     const uint32_t m_lo = (uint32_t)m, m_hi = (uint32_t)(m >> 32);
                     bool ok = r < DEAL_PAIR_LIMIT && !((m_lo & used_lo) | (m_hi & used_hi));
@@ -796,6 +807,23 @@ k_equity_mc_pool(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
                         sts_u16(cur, q);
                         cur = cur + kPoolRowBytes < end ? cur + kPoolRowBytes : end;     // full: later accepts of this round land in the spare row
                     }
+#else
+                    // -DPHE_POOL_SKIP_READS: a lane whose slots are full (or that has no sample left: cur is parked on end) skips
+                    // the table read.  Fewer shared-memory wavefronts (2.37e9 against 2.68e9 per 4.1e8 rollouts) but more
+                    // instructions (9.61e9 against 8.90e9): 3.84e10 against 3.91e10 rollouts/s on the B200 -- kept for the record
+                    bool need = cur != end;
+                    if (wi == 0) need = need && !skip01;
+                    uint32_t m_lo = 0xFFFFFFFFu, m_hi = 0xFFFFFFFFu;
+                    if (need) {
+                        const uint64_t m = dt.mask(q);
+                        m_lo = (uint32_t)m; m_hi = (uint32_t)(m >> 32);
+                    }
+                    if (r < DEAL_PAIR_LIMIT && !((m_lo & used_lo) | (m_hi & used_hi))) {
+                        used_lo |= m_lo; used_hi |= m_hi;
+                        sts_u16(cur, q);
+                        cur += kPoolRowBytes;
+                    }
+#endif
                 }
             }
             const bool done = live && (cur == end || blk == 63u);      // 64 blocks are never reached by a valid state; bounds garbage
@@ -816,6 +844,9 @@ k_equity_mc_pool(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
                     used_hi = live ? known_hi : 0xFFFFFFFFu;
                     cur = wcells + 2u * col;
                     end = cur + n_pairs * kPoolRowBytes;
+#ifdef PHE_POOL_SKIP_READS
+                    if (!live) cur = end;
+#endif
                 }
                 rf += cnt;
                 __syncwarp();

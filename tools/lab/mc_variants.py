@@ -14,8 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 VARIANTS = {
     "default": [],                                                   # k_equity_mc_pool: dealing decoupled from evaluation
+    "pool_skip_reads": ["-DPHE_POOL_SKIP_READS"],                    # ... finished lanes skip the pair-table read (fewer wavefronts, more instructions)
     "v1": ["-DPHE_MC_V1"],                                           # lock-step kernel: board-shared flush test, spare slot row, shared base in a register
-    "v1_remat_base": ["-DPHE_MC_V1", "-DPHE_MC_REMAT_BASE"],         # ... letting ptxas rebuild the shared-window base at every use
     "v1_round1_like": ["-DPHE_MC_V1", "-DPHE_MC_GENERIC_EVAL", "-DPHE_MC_REMAT_BASE"],
 }
 b = importlib.import_module("texasholdempocker-rl_b200.build")
