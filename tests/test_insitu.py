@@ -89,7 +89,7 @@ def test_install_rebinds_and_restores(reference_tree, phe):
     names = dropin.install(settle=True)
     try:
         assert game_mod.evaluate_cards is phe.evaluate_cards and workflow_mod.simulate_processes is phe.simulate_processes
-        assert game_mod.GameEnv.finish_game is not stock[2] and len(names) == 4
+        assert game_mod.GameEnv.finish_game is not stock[2] and len(names) == 5 and workflow_mod.predict_batch_process is phe.predict_batch_process
         with pytest.raises(RuntimeError):
             dropin.install()
     finally:

@@ -9,6 +9,7 @@ INTEGRATION.md describes:
   env/game.py:663-681   ``GameEnv.get_winner_set_v2``          -> ``winner.GameEnv.get_winner_set_v2``   (phe_showdown_host)
   env/game.py:410-441   ``GameEnv.finish_game``  (settle=True) -> ``settlement.settle_env``              (phe_settle_host)
   env/workflow.py:102   ``simulate_processes``                 -> ``service.simulate_processes``         (phe_equity_plan)
+  env/workflow.py:274   ``predict_batch_process``              -> ``predict_server.predict_batch_process`` (BatchedPredictor)
   env/env.py:416        ``Env.get_obs``          (encoder=...) -> ``ObsEncoder.get_obs``                 (phe_encode_obs)
   rl/MCTS.py:464-473    ``SingleThreadMCTS.predict`` (predictor=...) -> ``BatchedPredictor.predict``     (CUDA graph replay)
 
@@ -18,7 +19,7 @@ logged terminal with the same run on the stock (shim) evaluator.
 """
 import importlib
 
-from . import evaluator, service, settlement, winner
+from . import evaluator, predict_server, service, settlement, winner
 
 _saved = []
 
@@ -63,6 +64,7 @@ def install(predictor=None, encoder=None, settle=False, equity_service=True):
     if equity_service:
         workflow = importlib.import_module("env.workflow")
         _swap(workflow, "simulate_processes", service.simulate_processes)
+        _swap(workflow, "predict_batch_process", predict_server.predict_batch_process)
     if encoder is not None:
         env_mod = importlib.import_module("env.env")
         _swap(env_mod.Env, "get_obs", lambda self, infoset, mcts_acting_player_name=None: encoder.get_obs(infoset, mcts_acting_player_name))
