@@ -20,6 +20,7 @@
 #include <mutex>
 
 #include "../../include/phe_b200.h"
+#include "phe_attn_tc.cuh"
 
 void phe_internal_count_launch();          // phe_kernels.cu
 
@@ -538,6 +539,16 @@ extern "C" int phe_nn_attention(const void* q, const void* k, const void* v, voi
     });
     const auto *qp = static_cast<const __nv_bfloat16*>(q), *kp = static_cast<const __nv_bfloat16*>(k), *vp = static_cast<const __nv_bfloat16*>(v);
     auto* op = static_cast<__nv_bfloat16*>(out);
+#ifndef PHE_ATTN_LEGACY
+    if (head_dim == 64) {
+        // head dim 64 (config/default.yml): the tcgen05 / TMEM kernel (csrc/phe_attn_tc.cuh)
+        const cudaError_t e = phe_attn_tc::launch(qp, kp, vp, op, batch, heads, s_q, s_kv, q_batch_stride, q_row_stride, kv_batch_stride, kv_row_stride,
+                                                  scale_log2e, st);
+        if (e != cudaSuccess) { cudaGetLastError(); return PHE_ECUDA; }
+        phe_internal_count_launch();
+        return PHE_OK;
+    }
+#endif
     if (head_dim == 64)
         k_attention<64><<<blocks, kAttnWarps * 32, AttnSmem<64>::kBytes, st>>>(qp, kp, vp, op, total, heads, s_q, s_kv, q_batch_stride, q_row_stride, kv_batch_stride, kv_row_stride, scale_log2e);
     else
