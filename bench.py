@@ -2,7 +2,7 @@
 """bench.py -- headline benchmark of the hot path (BASELINE.json metric: MC equity rollouts/s at 1/2/4/8 B200; 7-card evals/s).
 
 Default step (BASELINE config 3): Monte-Carlo equity of S = 4096 random six-max game states, R = 1,000,000 rollouts per
-state, through k_equity_mc_pool.  With N GPUs the global sample range [0, R) of every state is split over the ranks and
+state, through k_equity_mc_smem.  With N GPUs the global sample range [0, R) of every state is split over the ranks and
 the int64[S,3] (win, tie, loss) counts are all-reduced inside the step: total work is fixed ("strong" scaling) and the
 counts are bit-identical for every N (checksum on the line).  Rank 0 prints ONE JSON line.
 
@@ -375,7 +375,7 @@ def main():
                 "value": S * R * steps / (total_ms * 1e-3), "e2e": {"value": S * R / e2e_s, "unit": "rollouts/s", "h2d_bytes_per_step": int(st_np.nbytes),
                                                                     "d2h_bytes_per_step": int(hw.nbytes), "ms_per_step": e2e_s * 1e3,
                                                                     "api": "phe.sharded_equity_mc(numpy states) -> numpy counts on every rank: H2D, "
-                                                                           "k_equity_mc_pool on the rank's sample shard, all_reduce, D2H"}}
+                                                                           "k_equity_mc_smem on the rank's sample shard, all_reduce, D2H"}}
 
     # ---- exhaustive enumeration (config 2) ----------------------------------------------------------------------------
     def enum_measure(steps):
@@ -428,6 +428,8 @@ def main():
         barrier()
         check("graph replay")
         total_ms = timed_steps(graph.replay, steps)
+        if fused is not None:
+            fused.check()                      # raises if a peer missed an exchange (the histogram of that step would be partial)
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
         scratch = torch.zeros(9 + 7463, dtype=torch.int64, device=dev)
         stream = torch.cuda.current_stream()
@@ -478,7 +480,7 @@ def main():
         if args.config == 3 and R == MC_ROLLOUTS:
             assert checksum == MC_CHECKSUM_1E6, f"win-count checksum {checksum} != {MC_CHECKSUM_1E6}"
         per_rank_units_per_s = m["shard_rollouts"] / (m["kern_ms"] * 1e-3)
-        roof = int_roofline("k_equity_mc_pool" if args.config != 1 else "k_equity_mc_gmem", per_rank_units_per_s, "rollout", m["kern_ms"],
+        roof = int_roofline("k_equity_mc_smem" if args.config != 1 else "k_equity_mc_gmem", per_rank_units_per_s, "rollout", m["kern_ms"],
                             w_rollout_reference_model(m["states"], n_opp))
         value, total_ms, launches, e2e = m["value"], m["total_ms"], m["launches"], m["e2e"]
         metric, unit = "mc_equity_rollouts_per_s", "rollouts/s"

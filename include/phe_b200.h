@@ -93,11 +93,14 @@ int phe_enum7_part(uint64_t *hist9, uint64_t *hist7463, uint64_t comb_begin, uin
  * out_hist7472 (device pointer, local).  peer_ws[r] is rank r's workspace (device pointer valid in this process:
  * CUDA IPC / torch symmetric memory), each phe_enum7_allreduce_workspace() bytes, zeroed once before first use.
  * The launch count (epoch) lives in the workspace, so the call may be captured in a CUDA graph and replayed; all
- * ranks must issue the same sequence of calls.  A peer that does not show up within ~2 s makes bin 0 of the output
- * UINT64_MAX instead of hanging. */
+ * ranks must issue the same sequence of calls.  A peer that does not show up within ~2 s does not hang the kernel: the
+ * output then holds a PARTIAL sum and the launch number is recorded in a status word of the workspace, which
+ * phe_enum7_allreduce_status reads back (synchronises `stream`): *launches_out = launches completed on this rank,
+ * *failed_launch_out = number of the last launch whose exchange timed out (0 = none so far). */
 uint64_t phe_enum7_allreduce_workspace(void);
 int phe_enum7_allreduce(uint64_t *out_hist7472, uint64_t comb_begin, uint64_t comb_end, int rank, int world,
                         void *const *peer_ws, void *stream);
+int phe_enum7_allreduce_status(const void *my_ws, void *stream, uint32_t *launches_out, uint32_t *failed_launch_out);
 
 /* ---- Monte-Carlo equity ------------------------------------------------- */
 /* For each state: deal the missing board cards and two cards to each of n_opp

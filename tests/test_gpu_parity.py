@@ -153,6 +153,26 @@ def test_equity_mc_bit_exact_vs_oracle(phe, oracle, torch):
         assert (got.sum(1) == rollouts).all()
 
 
+@pytest.mark.parametrize("n_opp,rollouts", [(8, 20011), (5, 24997), (1, 30000)])
+def test_equity_mc_large_launch_bit_exact_vs_oracle(phe, oracle, torch, n_opp, rollouts):
+    """>= 1e6 rollouts per launch: the persistent shared-memory kernel (k_equity_mc_smem; also what the -DPHE_MC_POOL
+    experiment build runs here).  Every street, ragged rollout counts, a sample offset, per-state opponent overrides, items
+    interleaved over the states -- counts equal the oracle's, state by state."""
+    states = phe.random_states(56, 77)
+    over = np.zeros(56, dtype=np.int64)
+    over[5::7] = (n_opp % 7) + 1                                     # some states carry their own opponent count
+    states[:, 1] = (states[:, 1].astype(np.uint64) | (over.astype(np.uint64) << np.uint64(61))).astype(np.int64)
+    before = phe._native.launch_count()
+    got = phe.equity_mc(torch.from_numpy(states).cuda(), n_opp, rollouts, seed=0x5EED20261019, sample_offset=12345, state_index_base=9).cpu().numpy()
+    assert phe._native.launch_count() == before + 1 and 56 * rollouts >= 1_000_000
+    assert (got.sum(1) == rollouts).all()
+    hero_mask = np.uint64(0x1FFF1FFF1FFF1FFF)
+    for s in range(56):
+        k = int(over[s]) or n_opp
+        want = oracle.equity_mc(int(states[s, 0]), int(np.uint64(states[s, 1]) & hero_mask), k, rollouts, 0x5EED20261019, sample_offset=12345, state_idx=9 + s)
+        assert (got[s] == want).all(), (s, k)
+
+
 def test_equity_mc_config1_single_state(phe, oracle, torch):
     # SURVEY 8d config 1: heads-up, hero As Ah, pre-flop and on flop 2c 7d Tc, 10k rollouts, seed 20261019
     st = phe.pack_states([["As", "Ah"], ["As", "Ah"]], [[], ["2c", "7d", "Tc"]])
@@ -359,6 +379,7 @@ def test_enum7_fused_allreduce_single_rank(phe, oracle, torch):
         g.replay()
     torch.cuda.synchronize()
     assert fe.out[:9].tolist() == gold["hist9"] and fe.out[9:].tolist() == gold["hist7463"]
+    assert fe.check() == 8          # launches completed (3 + 1 eager, 4 replays; the capture itself launches nothing); no exchange timed out
 
 
 def test_concurrent_callers(phe, oracle, torch):

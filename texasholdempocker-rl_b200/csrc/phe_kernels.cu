@@ -337,13 +337,14 @@ __device__ __forceinline__ void enum_allreduce_epilogue(const FusedArgs& fa)
             if (clock64() - t0 > 4000000000ll) { ok = false; break; }   // ~2 s: a peer never launched
             __nanosleep(200);
         }
-        if (!ok) fa.out[0] = ~0ull;
+        // a late peer leaves a PARTIAL sum: recorded per launch in a status word of its own (epoch_p[1] = the launch
+        // number that failed; never a histogram bin), read by phe_enum7_allreduce_status / FusedEnum7.check()
+        if (!ok) atomicExch(epoch_p + 1, e);
     }
     __syncthreads();
     __threadfence_system();
     // 4. sum the slots (again: all loads of a bin group in flight together)
     const unsigned char* base = my + kWsSlots + (size_t)(e & 1u) * kMaxWorld * kAllBins * 8;
-    const bool failed = fa.out[0] == ~0ull;
     unsigned long long sum[kPer];
 #pragma unroll
     for (int k = 0; k < kPer; k++) sum[k] = 0;
@@ -358,7 +359,7 @@ __device__ __forceinline__ void enum_allreduce_epilogue(const FusedArgs& fa)
 #pragma unroll
     for (int k = 0; k < kPer; k++) {
         const int i = threadIdx.x + k * kCtaThreads;
-        if (i < kAllBins && !(failed && i == 0)) fa.out[i] = sum[k];
+        if (i < kAllBins) fa.out[i] = sum[k];
     }
     if (threadIdx.x == 0) *epoch_p = e;
 }
@@ -573,7 +574,9 @@ __device__ __forceinline__ void equity_mc_body(const Tab& tab, const DealTab& dt
             item = __shfl_sync(0xFFFFFFFFu, nxt, 0);
         }
         if (item >= items) break;
-        const uint64_t s = item / chunks_per_state, ch = item - s * chunks_per_state;
+        // consecutive items belong to DIFFERENT states: warps that run side by side then work on different streets, whose
+        // dealing / evaluation mix differs -- a batch of few states with many chunks each would otherwise run one state at a time
+        const uint64_t ch = item / (uint64_t)n_states, s = item - ch * (uint64_t)n_states;
         const ulonglong2 st = states[s];
         const uint64_t known = st.x & CARD_BITS, hero = st.y & CARD_BITS;
         const int over = (int)(st.y >> 61);
@@ -629,8 +632,9 @@ k_equity_mc_smem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
     }
 }
 
+#ifdef PHE_MC_POOL
 // ------------------------------------------------------------------------------------------------
-// K3 (round 2): Monte-Carlo equity with dealing decoupled from evaluation.
+// K3, experiment of round 2 (compiled with -DPHE_MC_POOL only): Monte-Carlo equity with dealing decoupled from evaluation.
 //
 // In the kernel above a warp deals 32 samples in lock step and waits for its slowest lane: rejection sampling needs a
 // different number of draws per sample, so the dealing loop -- 60 % of the instructions -- ran at ~20 of 32 lanes (ncu:
@@ -640,7 +644,14 @@ k_equity_mc_smem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
 // column holding its accepted slots on the warp's READY ring, takes a free column and starts its next sample in the
 // following round; whenever 32 deals are ready the warp evaluates them together, lane j taking the j-th ready column --
 // evaluation always runs on 32 lanes, whoever dealt the hands.  The deal of (state, sample) and therefore every count
-// is unchanged (same stream contract as deal_slots / the oracle).
+// is unchanged (same stream contract as deal_slots / the oracle; tests/test_gpu_parity.py passes with either kernel).
+//
+// Outcome on the B200 (profiles/mc_streets_r02.jsonl, profiles/ncu_mc_r02_pool.json): 30.1 of 32 lanes active instead of
+// 25.4 and 9 % fewer instructions, but every lane now reads the pair table for all eight draws of a round: 25 % more
+// shared-memory wavefronts, 87 % of the wavefront rate -- the bound moved from the issue slots to shared memory.  Equal
+// to the lock-step kernel on the mixed six-max batch of BASELINE config 3 (3.894e10 against 3.886e10 rollouts/s), 8 %
+// faster on river-only six-max batches, 7-17 % slower on the other streets and 12 % slower heads-up.  The lock-step
+// kernel therefore stays the product path.
 //
 // Per warp: 64 columns x 12 rows of u16 cells (rows 0..9 pair slots, row n_pairs doubles as the spare row of the
 // clamped cursor, row 11 the single card) = [row][64] so that any 32 distinct columns are bank-conflict free, plus a
@@ -699,7 +710,7 @@ k_equity_mc_pool(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
         if (lane == 0) nxt = atomicAdd(counters, 1u);
         const uint64_t item = __shfl_sync(0xFFFFFFFFu, nxt, 0);
         if (item >= items) break;
-        const uint64_t s = item / chunks_per_state, ch = item - s * chunks_per_state;
+        const uint64_t ch = item / (uint64_t)n_states, s = item - ch * (uint64_t)n_states;      // interleaved over the states (see equity_mc_body)
         const ulonglong2 st = states[s];
         const uint64_t known = st.x & CARD_BITS, hero = st.y & CARD_BITS;
         const int over = (int)(st.y >> 61);
@@ -871,6 +882,8 @@ k_equity_mc_pool(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
         counters[1] = 0;
     }
 }
+
+#endif   // PHE_MC_POOL
 
 __global__ void __launch_bounds__(256)
 k_equity_mc_gmem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict__ g_dealtab, const ulonglong2* __restrict__ states,
@@ -1224,7 +1237,9 @@ void init_device(int device)
     chk(cudaFuncSetAttribute(k_eval7_smem<PHE_LAYOUT_MASKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr eval7 masks");
     chk(cudaFuncSetAttribute(k_enum7, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEnum), "attr enum7");
     chk(cudaFuncSetAttribute(k_equity_mc_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMc), "attr equity_mc");
+#ifdef PHE_MC_POOL
     chk(cudaFuncSetAttribute(k_equity_mc_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMcPool), "attr equity_mc_pool");
+#endif
     chk(cudaFuncSetAttribute(k_equity_plan_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr equity_plan");
     chk(cudaFuncSetAttribute(k_showdown_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTabOnly), "attr showdown");
 }
@@ -1473,6 +1488,18 @@ int phe_enum7_allreduce(uint64_t* out_hist7472, uint64_t comb_begin, uint64_t co
     return launch_enum7(acc, acc + 9, comb_begin, comb_end, (uint32_t)rank, (uint32_t)world, fa, stream);
 }
 
+int phe_enum7_allreduce_status(const void* my_ws, void* stream, uint32_t* launches_out, uint32_t* failed_launch_out)
+{
+    if (!my_ws || !launches_out || !failed_launch_out) return PHE_EINVAL;
+    uint32_t words[2] = {0, 0};    // {epoch = launches completed, launch number of the last exchange that timed out (0 = none)}
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PHE_CUDA(cudaMemcpyAsync(words, static_cast<const unsigned char*>(my_ws) + kWsEpoch, sizeof words, cudaMemcpyDeviceToHost, st));
+    PHE_CUDA(cudaStreamSynchronize(st));
+    *launches_out = words[0];
+    *failed_launch_out = words[1];
+    return PHE_OK;
+}
+
 int phe_enum7(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin, uint64_t comb_end, void* stream)
 {
     return phe_enum7_part(hist9, hist7463, comb_begin, comb_end, 0, 1, stream);
@@ -1534,10 +1561,10 @@ int phe_equity_mc(const uint64_t* states, int64_t n_states, int n_opp, uint64_t 
         uint64_t ctas = (items + kMcThreads / 32 - 1) / (kMcThreads / 32);
         if (ctas > (uint64_t)cx->sm_count) ctas = cx->sm_count;
         unsigned int* counters = cx->d_counters + 2 * (cx->next_counter.fetch_add(1, std::memory_order_relaxed) % kCounterRing);
-#ifdef PHE_MC_V1
-        k_equity_mc_smem<<<(unsigned)ctas, kMcThreads, kSmemMc, st>>>(cx->d_image, cx->d_pairmask, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk, counters);
-#else
+#ifdef PHE_MC_POOL
         k_equity_mc_pool<<<(unsigned)ctas, kCtaThreads, kSmemMcPool, st>>>(cx->d_image, cx->d_pairmask, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk, counters);
+#else
+        k_equity_mc_smem<<<(unsigned)ctas, kMcThreads, kSmemMc, st>>>(cx->d_image, cx->d_pairmask, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk, counters);
 #endif
     }
     return after_launch("equity_mc launch");

@@ -106,3 +106,15 @@ class FusedEnum7:
         N.check(N.lib().phe_enum7_allreduce(C.c_void_p(self.out.data_ptr()), comb_begin, comb_end, self.rank, self.world, self._ptrs,
                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return self.out[:9], self.out[9:]
+
+    def check(self):
+        """Synchronises the current stream and raises if a peer did not show up in time for any exchange so far (the output of
+        that launch is a partial sum); returns the number of launches completed on this rank."""
+        import ctypes as C
+        launches, failed = C.c_uint32(0), C.c_uint32(0)
+        N.check(N.lib().phe_enum7_allreduce_status(C.c_void_p(self.ws.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream),
+                                                   C.byref(launches), C.byref(failed)))
+        if failed.value:
+            raise N.PheError(f"fused enumeration all-reduce: a peer did not arrive within the time-out at launch {failed.value} "
+                             f"(rank {self.rank} of {self.world}); the histogram of that launch is partial")
+        return int(launches.value)

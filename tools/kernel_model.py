@@ -13,8 +13,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # kernel -> (summary file candidates newest first, kernel-name substring, units in the profiled launch, unit)
 SOURCES = {
-    "k_equity_mc_pool": (["ncu_mc_r02.json"], "k_equity_mc_pool", 4096 * 100000, "rollout"),                          # tools/prof_driver.py mc
-    "k_equity_mc_smem": (["ncu_mc_r02_lockstep.json", "ncu_mc_r01.json"], "k_equity_mc_smem", 4096 * 100000, "rollout"),   # the round-1 lock-step kernel (-DPHE_MC_V1)
+    "k_equity_mc_smem": (["ncu_mc_r02.json", "ncu_mc_r02_lockstep.json", "ncu_mc_r01.json"], "k_equity_mc_smem", 4096 * 100000, "rollout"),   # tools/prof_driver.py mc
+    "k_equity_mc_pool": (["ncu_mc_r02_pool.json"], "k_equity_mc_pool", 4096 * 100000, "rollout"),                     # the decoupled experiment (-DPHE_MC_POOL)
     "k_enum7": (["ncu_enum7_r02.json", "ncu_enum7_r01.json"], "k_enum7", 133784560, "hand"),                          # tools/prof_driver.py enum
     "k_eval7_smem": (["ncu_eval7_r02.json", "ncu_eval7_r01.json"], "k_eval7_smem", 1 << 25, "hand"),
 }
