@@ -662,11 +662,7 @@ def mcts_selfplay(phe, torch, n_simulation=800, moves=4):
     out = {"config": {"workload": "MCTS self-play (BASELINE config 4)", "simulations_per_move": n_simulation, "players": 2, "blinds": "25/50",
                       "model": "config/debug.yml dims (d=96, 2 layers), random init, fp32", "moves_timed": moves}}
     terminals = [0]
-    inner = game_mod.GameEnv.finish_game
-
-    def counting_finish(self):
-        terminals[0] += 1
-        return type(self).__dict__["_phe_bench_inner"](self)
+    stock_finish = game_mod.GameEnv.finish_game
     # (a) unpatched reference, fewer simulations per move (it is ~100x slower; the rate is what is reported)
     _, _, _, env_a = R.build_model_and_env()
     sims, dt, mv = R.mcts_moves(env_a, lambda: R.make_search("reference", params, mp_, model, max(50, n_simulation // 8)), 2, 3)
@@ -675,7 +671,11 @@ def mcts_selfplay(phe, torch, n_simulation=800, moves=4):
     # (b) the same search with every drop-in installed
     dropin.install(predictor=predictor, encoder=encoder, settle=True)
     try:
-        game_mod.GameEnv._phe_bench_inner = game_mod.GameEnv.finish_game
+        settle_finish = game_mod.GameEnv.finish_game            # the drop-in (phe_settle)
+
+        def counting_finish(self):
+            terminals[0] += 1
+            return settle_finish(self)
         game_mod.GameEnv.finish_game = counting_finish
         r0 = predictor.replays
         _, _, _, env_b = R.build_model_and_env()
@@ -684,10 +684,9 @@ def mcts_selfplay(phe, torch, n_simulation=800, moves=4):
                                     "simulations_per_move": n_simulation // 4, "moves": mv,
                                     "what": "reference SingleThreadMCTS + Env with dropin.install(predictor, encoder, settle=True): one GPU round trip per leaf stage"}
     finally:
-        game_mod.GameEnv.finish_game = game_mod.GameEnv._phe_bench_inner
-        del game_mod.GameEnv._phe_bench_inner
+        game_mod.GameEnv.finish_game = settle_finish
         dropin.uninstall()
-    assert game_mod.GameEnv.finish_game is inner
+    assert game_mod.GameEnv.finish_game is stock_finish
     # (c) lock-step waves
     backends = GpuBackends(predictor, encoder, seed=STATE_SEED)
     stats = WaveMCTS(mp_["num_output_class"], params["small_blind"], backends).stats          # one counter set shared by every move's search

@@ -50,7 +50,13 @@ class GpuBackends:
 
     def __init__(self, predictor, encoder, seed=0):
         self.predictor, self.encoder, self.seed = predictor, encoder, seed
+        self.stream = 0                                              # Philox stream of the current search: one per simulate() call
         self._deck = importlib.import_module("env.game").deck        # deck[i] is the card with id i (env/game.py:14-18)
+
+    def new_search(self):
+        """Called by WaveMCTS at the start of every search: two searches never replay the same re-deals, even when the
+        acting player sees the same cards (two decisions on one street)."""
+        self.stream = (self.stream + 1) & 0xFFFFFFFF
 
     def deal(self, game_env, n, first_simulation):
         """n re-deals of what the acting player cannot see -> list of (hands of the other seats in ``info_sets`` order,
@@ -64,7 +70,7 @@ class GpuBackends:
         if game_env.current_round >= 3:
             shown += list(game_env.river_cards)
         opp, board = determinise(game_env.info_sets[acting].player_hand_cards, shown, game_env.num_players, n, self.seed,
-                                 sample_offset=first_simulation)
+                                 sample_offset=first_simulation, stream=self.stream)
         d = self._deck
         out = []
         for i in range(n):
@@ -160,6 +166,8 @@ class WaveMCTS:
         game_env = env._env
         acting = game_env.acting_player_name
         root = self.root = self._node(True)
+        if hasattr(self.backends, "new_search"):
+            self.backends.new_search()
         probs, values = self.backends.predict_batch(np.asarray(observation, dtype=np.int32).reshape(1, -1))
         st["nn_calls"] += 1
         st["nn_rows"] += 1
