@@ -299,7 +299,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
 }
 
 // executed by the last CTA of the launch, after every CTA's flush into acc is visible
-__device__ __forceinline__ void enum_allreduce_epilogue(const FusedArgs& fa)
+__device__ __noinline__ void enum_allreduce_epilogue(const FusedArgs& fa)   // not inlined: keeps the register allocation of the enumeration loop independent of this once-per-launch code
 {
     unsigned char* my = fa.ws[fa.rank];
     unsigned long long* acc = reinterpret_cast<unsigned long long*>(my + kWsAcc);
