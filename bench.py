@@ -641,6 +641,57 @@ def single_gpu_extras(phe, torch, np, dev):
     return out
 
 
+def _farm_worker(rank, barrier, queue, n_simulation, moves):
+    """One self-play process of the farm: its own CUDA context on cuda:0, the wave driver on the reference's Env."""
+    import torch
+    import texasholdempocker_rl_b200 as phe
+    from baseline import ref_arm as R
+    from texasholdempocker_rl_b200.mcts_wave import GpuBackends, WaveMCTS
+    R.setup_paths()
+    from env.constants import ChoiceMethod
+    torch.set_num_threads(1)
+    torch.cuda.set_device(0)
+    params, mp_, model, env = R.build_model_and_env(seed=rank)
+    net = phe.PolicyValueNet(**mp_)
+    net.load_reference_state_dict(model.state_dict())
+    predictor = phe.BatchedPredictor(net, dtype=torch.float32, max_batch=64, buckets=[1, 8, 64])
+    predictor.warmup()
+    backends = GpuBackends(predictor, phe.ObsEncoder(mp_["num_output_class"], mp_["historical_action_per_round"]), seed=STATE_SEED + rank)
+
+    def make_wave():
+        return WaveMCTS(mp_["num_output_class"], params["small_blind"], backends, n_simulation=n_simulation, c_puct=params["mcts_c_puct"],
+                        tau=params["mcts_tau"], model_Q_epsilon=params["mcts_model_Q_epsilon"], choice_method=ChoiceMethod(params["mcts_choice_method"]), wave=64)
+    R.mcts_moves(env, make_wave, 1, 100 + rank)                  # warm-up move: kernels loaded, graphs captured
+    barrier.wait()
+    t0 = time.perf_counter()
+    sims, dt, mv = R.mcts_moves(env, make_wave, moves, 200 + rank)
+    queue.put((rank, sims, t0, t0 + dt))
+
+
+def mcts_farm(workers, n_simulation=800, moves=3):
+    """The reference runs its game loops in many processes (main.py:140-147); so does this: `workers` self-play processes
+    share ONE GPU, each with the lock-step wave driver.  Aggregate simulations/s = all simulations / (last finish - first start)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    barrier, queue = ctx.Barrier(workers), ctx.Queue()
+    procs = [ctx.Process(target=_farm_worker, args=(r, barrier, queue, n_simulation, moves), daemon=True) for r in range(workers)]
+    for p in procs:
+        p.start()
+    rows = []
+    try:
+        for _ in procs:
+            rows.append(queue.get(timeout=300))
+    finally:
+        for p in procs:
+            p.join(timeout=10)
+            if p.is_alive():
+                p.kill()
+    sims = sum(r[1] for r in rows)
+    span = max(r[3] for r in rows) - min(r[2] for r in rows)
+    return {"workers": workers, "simulations_per_s": sims / span, "simulations": sims, "seconds": span, "moves_per_worker": moves,
+            "what": "self-play processes sharing one B200 (own CUDA context each), WaveMCTS with 64 simulations per wave, debug.yml parameters"}
+
+
 def mcts_selfplay(phe, torch, n_simulation=800, moves=4):
     """config/debug.yml game parameters (800 simulations per move, heads-up, blinds 25/50, debug model dims).
     Three searches over the same seeded self-play: (a) the unpatched reference on the host (CPU model, shim evaluator),
@@ -701,6 +752,10 @@ def mcts_selfplay(phe, torch, n_simulation=800, moves=4):
                    "nn_calls_per_s": stats["nn_calls"] / dt, "wave": 64, "simulations_per_move": n_simulation, "moves": mv,
                    "seconds_by_stage": {k[2:]: round(v, 4) for k, v in stats.items() if k.startswith("t_")},
                    "what": "mcts_wave.WaveMCTS: reference tree nodes + GameEnv.step on the host, determinise / encode / predict_batch / settle_envs batched per wave"}
+    try:
+        out["farm"] = mcts_farm(min(8, max(2, (os.cpu_count() or 2) // 2)))
+    except Exception as ex:  # noqa: BLE001
+        out["farm"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
     out["value"] = out["wave"]["simulations_per_s"]
     out["unit"] = "simulations/s"
     out["speedup_wave_vs_reference_cpu"] = out["wave"]["simulations_per_s"] / out["reference_cpu"]["simulations_per_s"]
