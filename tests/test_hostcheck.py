@@ -125,6 +125,31 @@ def test_enum_block_walk_full(hostcheck):
     assert h.tolist() == json.load(open(os.path.join(GOLDEN, "hist7463.json")))["hist7463"]
 
 
+def test_enum_work_units(hostcheck):
+    """build_enum_units (phe_tables.cpp): the enumeration kernel's tiles.  Units partition [0, C(52,7)), hold at most 512 hands
+    and at most 4 whole enumeration blocks (a block = one (c3..c6) suffix = C(c3,3) consecutive colex indices)."""
+    from math import comb
+    hostcheck.hc_enum_units.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int64]
+    hostcheck.hc_enum_units.restype = C.c_int64
+    buf = np.zeros(400000, dtype=np.uint32)
+    starts = np.zeros(400000, dtype=np.uint64)
+    n = hostcheck.hc_enum_units(512, 4, vp(buf), vp(starts), len(buf))
+    u = buf[:n].astype(np.int64)
+    assert u[0] == 0 and u[-1] == 133784560 and (np.diff(u) > 0).all() and np.diff(u).max() <= 512
+    sizes = np.array([comb(c3, 3) for c6 in range(6, 52) for c5 in range(5, c6) for c4 in range(4, c5) for c3 in range(3, c4)], dtype=np.int64)
+    ends = np.cumsum(sizes)                                            # block ends on the colex axis
+    starts_in = np.searchsorted(ends, u[1:], side="right") - np.searchsorted(ends, u[:-1], side="right")   # block ends inside each unit
+    assert starts_in.max() <= 4
+    assert n < 300000                                                  # ~1.1 MB + 2.2 MB tables
+    # the packed start of every unit is the colex unranking of its first index
+    st = starts[:n - 1].astype(np.int64)
+    c3, c4, c5, c6, tri = st & 63, (st >> 6) & 63, (st >> 12) & 63, (st >> 18) & 63, st >> 24
+    c4t = np.array([comb(v, 4) for v in range(53)]); c5t = np.array([comb(v, 5) for v in range(53)])
+    c6t = np.array([comb(v, 6) for v in range(53)]); c7t = np.array([comb(v, 7) for v in range(53)]); c3t = np.array([comb(v, 3) for v in range(53)])
+    assert (c3 < c4).all() and (c4 < c5).all() and (c5 < c6).all() and (c6 < 52).all() and (tri < c3t[c3]).all()
+    assert (tri + c4t[c3] + c5t[c4] + c6t[c5] + c7t[c6] == u[:-1]).all()
+
+
 def test_multiply_shift_reductions_are_exact():
     """phe_core.cuh mod1326_u16 / mod52_u16: exact for every 16-bit input."""
     r = np.arange(65536, dtype=np.uint64)

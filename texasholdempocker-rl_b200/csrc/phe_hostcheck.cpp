@@ -138,6 +138,19 @@ void hc_settle(uint64_t board, const uint64_t* holes, int P, int R, int button, 
     settle_game(P, R, button, small_blind, onboard, ranks, act, val, won, result, card, paid);
 }
 
+// work-unit boundaries of the enumeration kernel (build_enum_units); returns the count, copies at most `cap` entries
+int64_t hc_enum_units(uint32_t max_hands, uint32_t max_blocks, uint32_t* out, uint64_t* starts_out, int64_t cap)
+{
+    std::vector<uint32_t> u;
+    std::vector<uint64_t> st;
+    build_enum_units(u, st, max_hands, max_blocks);
+    for (int64_t i = 0; i < (int64_t)u.size() && i < cap; i++) {
+        out[i] = u[(size_t)i];
+        starts_out[i] = st[(size_t)i];
+    }
+    return (int64_t)u.size();
+}
+
 uint64_t hc_plan_num_deals(int n_exist, const int32_t* plan, int n_steps)
 {
     PlanDesc pd;

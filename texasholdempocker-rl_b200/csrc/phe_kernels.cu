@@ -8,6 +8,7 @@
 // compute path: every entry point either launches a kernel or returns an error.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -271,18 +272,25 @@ __device__ __forceinline__ uint32_t enum_flush_addr(uint32_t x, uint32_t t, uint
 }
 
 // ---- fused all-reduce epilogue (phe_enum7_allreduce) --------------------------------------------------------
+// In fused mode every CTA adds its 30 KB shared-memory histogram (u32 bins; a whole C(52,7) bin fits 32 bits) into a
+// per-launch u32 array in global memory with ONE TMA bulk reduction (cp.reduce.async.bulk .add.u32: the adds are performed
+// by the L2, no thread touches a bin).  The last CTA of the launch pushes that array to the peers, sums what the peers
+// pushed, and clears it for the next launch.  (The plain kernel keeps per-CTA 64-bit REDs straight into the caller's
+// histograms: with no exchange to feed, a second level only adds a serial pass -- measured 2 us slower.)
+//
 // Workspace of one rank (all ranks use the same layout; peers write into it through NVLink):
-//   slots  u64[2][8][7472]   histogram of source rank s for launches of parity p
+//   slots  u32[2][8][7464]   payload (bins, one pad word) of source rank s for launches of parity p
 //   flags  u32[8]            flags[s] = number of the last launch whose slot from rank s is complete
-//   acc    u64[7472]         local accumulation target of the CTA flushes (zero between launches)
-//   epoch  u32               launch number (starts at 0 -> first launch is 1)
-constexpr int kAllBins = 9 + kHistBins;                       // 7472
+//   epoch  u32, failed u32   launch number (starts at 0 -> first launch is 1); launch number of a timed-out exchange
+constexpr int kAllBins = 9 + kHistBins;                       // 7472 (layout of the u64 result: hist9 then hist7463)
+static_assert(kAllBins == 7472, "phe_enum7_allreduce writes out_hist7472");
 constexpr int kMaxWorld = 8;
+constexpr int kSlotWords = kHistBinsPad;                      // 7464 u32 = 1866 uint4
 constexpr size_t kWsSlots = 0;
-constexpr size_t kWsFlags = kWsSlots + (size_t)2 * kMaxWorld * kAllBins * 8;
-constexpr size_t kWsAcc = kWsFlags + 64;
-constexpr size_t kWsEpoch = kWsAcc + (size_t)kAllBins * 8;
-constexpr size_t kWsBytes = kWsEpoch + 64;
+constexpr size_t kWsFlags = kWsSlots + (size_t)2 * kMaxWorld * kSlotWords * 4;
+constexpr size_t kWsEpoch = kWsFlags + 64;
+constexpr size_t kWsBytes = kWsEpoch + 128;                   // epoch, failed, then (PHE_ENUM_PROF) eight %globaltimer stamps
+static_assert(kSlotWords % 4 == 0 && kWsFlags % 16 == 0, "uint4 access to the slots");
 
 struct FusedArgs {
     int rank, world;                       // world == 0: plain kernel, results go to hist9 / hist7463
@@ -297,79 +305,135 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#ifdef PHE_ENUM_PROF
+#define PHE_ENUM_STAMP(ws, k) do { if (threadIdx.x == 0) reinterpret_cast<unsigned long long*>((ws) + kWsEpoch + 16)[k] = globaltimer_ns(); } while (0)
+__device__ unsigned long long g_enum_prof[256 * 4];   // per CTA of the last launch: start, tables staged, loop done, flush done
+#define PHE_ENUM_CTA_STAMP(k) do { if (threadIdx.x == 0) g_enum_prof[blockIdx.x * 4 + (k)] = globaltimer_ns(); } while (0)
+#else
+#define PHE_ENUM_STAMP(ws, k) do { } while (0)
+#define PHE_ENUM_CTA_STAMP(k) do { } while (0)
+#endif
 
-// executed by the last CTA of the launch, after every CTA's flush into acc is visible
-__device__ __noinline__ void enum_allreduce_epilogue(const FusedArgs& fa)   // not inlined: keeps the register allocation of the enumeration loop independent of this once-per-launch code
+constexpr int kHistVec = kHistBinsPad / 4;                              // 1866 uint4 groups of bins
+constexpr int kVecPer = (kHistVec + kCtaThreads - 1) / kCtaThreads;     // 2 per thread
+
+// Executed by the last CTA: push this rank's u32 payload into its slot on every rank, signal, wait for the peers' slots,
+// sum.  Ordering follows the usual one-thread pattern: the payload stores of all threads are ordered before the flag by
+// bar.sync + st.release.sys of the signalling threads (release is cumulative), and the peers' payloads are ordered after
+// ld.acquire.sys + bar.sync on the reading side; no other thread issues a system-scope fence.
+__device__ __noinline__ void enum_allreduce_epilogue(const FusedArgs& fa, uint32_t* g_h32, uint32_t* s_h9)
 {
     unsigned char* my = fa.ws[fa.rank];
-    unsigned long long* acc = reinterpret_cast<unsigned long long*>(my + kWsAcc);
     uint32_t* epoch_p = reinterpret_cast<uint32_t*>(my + kWsEpoch);
     const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_p) + 1u;
-    const size_t slot_off = kWsSlots + ((size_t)(e & 1u) * kMaxWorld + (size_t)fa.rank) * kAllBins * 8;
-    // 1. push this rank's histogram into its slot on every rank (peer stores), clear acc for the next launch.
-    //    All loads are issued before the first store so that the L2 round trips overlap.
-    constexpr int kPer = (kAllBins + kCtaThreads - 1) / kCtaThreads;   // 8 bins per thread
+    const size_t slot_off = kWsSlots + ((size_t)(e & 1u) * kMaxWorld + (size_t)fa.rank) * kSlotWords * 4;
+    const int world = fa.world;
+    unsigned long long* const out = fa.out;
+    PHE_ENUM_STAMP(my, 1);
+    // 1. payload -> slot (e, rank) of every rank; g_h32 cleared for the next launch.  Loads first, then the stores.
     {
-        unsigned long long v[kPer];
+        uint4 v[kVecPer];
 #pragma unroll
-        for (int k = 0; k < kPer; k++) {
-            const int i = threadIdx.x + k * kCtaThreads;
-            v[k] = i < kAllBins ? __ldcg(acc + i) : 0ull;
+        for (int k = 0; k < kVecPer; k++) {
+            const int g = threadIdx.x + k * kCtaThreads;
+            v[k] = g < kHistVec ? __ldcg(reinterpret_cast<const uint4*>(g_h32) + g) : make_uint4(0, 0, 0, 0);
         }
+#pragma unroll 1   // once-per-launch code runs from a cold instruction cache: compact beats unrolled here
+        for (int p = 0; p < world; p++) {
+            uint4* dst = reinterpret_cast<uint4*>(fa.ws[p] + slot_off);
 #pragma unroll
-        for (int k = 0; k < kPer; k++) {
-            const int i = threadIdx.x + k * kCtaThreads;
-            if (i < kAllBins) {
-                acc[i] = 0;
-                for (int p = 0; p < fa.world; p++) reinterpret_cast<unsigned long long*>(fa.ws[p] + slot_off)[i] = v[k];
+            for (int k = 0; k < kVecPer; k++) {
+                const int g = threadIdx.x + k * kCtaThreads;
+                if (g < kHistVec) dst[g] = v[k];
             }
         }
+#pragma unroll
+        for (int k = 0; k < kVecPer; k++) {
+            const int g = threadIdx.x + k * kCtaThreads;
+            if (g < kHistVec) reinterpret_cast<uint4*>(g_h32)[g] = make_uint4(0, 0, 0, 0);
+        }
     }
-    __threadfence_system();
     __syncthreads();
+    PHE_ENUM_STAMP(my, 2);
     // 2. tell every rank that slot (e, rank) is complete; 3. wait until all of this rank's slots of launch e are
-    if ((int)threadIdx.x < fa.world) {
+    if ((int)threadIdx.x < world) {
         st_release_sys(reinterpret_cast<uint32_t*>(fa.ws[threadIdx.x] + kWsFlags) + fa.rank, e);
         const uint32_t* mine = reinterpret_cast<const uint32_t*>(my + kWsFlags) + threadIdx.x;
         const long long t0 = clock64();
         bool ok = true;
         while ((int32_t)(ld_acquire_sys(mine) - e) < 0) {
             if (clock64() - t0 > 4000000000ll) { ok = false; break; }   // ~2 s: a peer never launched
-            __nanosleep(200);
+            __nanosleep(64);
         }
         // a late peer leaves a PARTIAL sum: recorded per launch in a status word of its own (epoch_p[1] = the launch
         // number that failed; never a histogram bin), read by phe_enum7_allreduce_status / FusedEnum7.check()
         if (!ok) atomicExch(epoch_p + 1, e);
     }
     __syncthreads();
-    __threadfence_system();
-    // 4. sum the slots (again: all loads of a bin group in flight together)
-    const unsigned char* base = my + kWsSlots + (size_t)(e & 1u) * kMaxWorld * kAllBins * 8;
-    unsigned long long sum[kPer];
+    PHE_ENUM_STAMP(my, 3);
+    // 4. sum the slots (all loads of a group in flight together), widen to the u64 result: hist9 at [0, 9), bins at [9, 7472).
+    //    The nine category counts are segment sums of the summed bins: bins are ordered by category, so a warp's 128
+    //    consecutive bins nearly always lie in one category -> one warp reduction and one shared atomic per warp.
+    const unsigned char* base = my + kWsSlots + (size_t)(e & 1u) * kMaxWorld * kSlotWords * 4;
+    unsigned long long sum[kVecPer][4];
 #pragma unroll
-    for (int k = 0; k < kPer; k++) sum[k] = 0;
-    for (int s = 0; s < fa.world; s++) {
-        const unsigned long long* slot = reinterpret_cast<const unsigned long long*>(base + (size_t)s * kAllBins * 8);
+    for (int k = 0; k < kVecPer; k++) sum[k][0] = sum[k][1] = sum[k][2] = sum[k][3] = 0;
+#pragma unroll 2
+    for (int s = 0; s < world; s++) {                                  // slot loop outside: the loads of both groups fly together
+        const uint4* slot = reinterpret_cast<const uint4*>(base + (size_t)s * kSlotWords * 4);
 #pragma unroll
-        for (int k = 0; k < kPer; k++) {
-            const int i = threadIdx.x + k * kCtaThreads;
-            if (i < kAllBins) sum[k] += __ldcg(slot + i);
+        for (int k = 0; k < kVecPer; k++) {
+            const int g = threadIdx.x + k * kCtaThreads;
+            if (g < kHistVec) {
+                const uint4 w = __ldcg(slot + g);
+                sum[k][0] += w.x; sum[k][1] += w.y; sum[k][2] += w.z; sum[k][3] += w.w;
+            }
         }
     }
 #pragma unroll
-    for (int k = 0; k < kPer; k++) {
-        const int i = threadIdx.x + k * kCtaThreads;
-        if (i < kAllBins) fa.out[i] = sum[k];
+    for (int k = 0; k < kVecPer; k++) {
+        const int g = threadIdx.x + k * kCtaThreads;                  // whole warps take part in the reduction below
+        if (g < kHistVec) {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (4 * g + j < kHistBins) out[9 + 4 * g + j] = sum[k][j];
+        }
+        const int b0 = min(4 * g, kHistBins - 1), b3 = min(4 * g + 3, kHistBins - 1);
+        const int ca = category_of((uint32_t)b0), cb = category_of((uint32_t)b3);
+        const int c_first = __shfl_sync(0xFFFFFFFFu, ca, 0);
+        if (__all_sync(0xFFFFFFFFu, ca == c_first && cb == c_first)) {
+            const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)(sum[k][0] + sum[k][1] + sum[k][2] + sum[k][3]));   // < 2^32: at most C(52,7)
+            if ((threadIdx.x & 31) == 0 && tot) atomicAdd(s_h9 + c_first, tot);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (sum[k][j]) atomicAdd(s_h9 + category_of((uint32_t)min(4 * g + j, kHistBins - 1)), (uint32_t)sum[k][j]);
+        }
     }
+    PHE_ENUM_STAMP(my, 5);
+    __syncthreads();
+    PHE_ENUM_STAMP(my, 6);
+    if (threadIdx.x < 9) out[threadIdx.x] = s_h9[threadIdx.x];
     if (threadIdx.x == 0) *epoch_p = e;
+    PHE_ENUM_STAMP(my, 4);
 }
 
 __global__ void __launch_bounds__(kCtaThreads, 1)
 k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_trimask, unsigned long long* __restrict__ hist9,
-        unsigned long long* __restrict__ hist7463, uint64_t begin, uint64_t end, uint32_t tile_size, uint32_t ntiles,
-        unsigned int* __restrict__ tile_counter, uint32_t part, uint32_t nparts, FusedArgs fa)
+        unsigned long long* __restrict__ hist7463, uint64_t begin, uint64_t end, const uint32_t* __restrict__ g_units, const uint64_t* __restrict__ g_unit_starts, uint32_t unit_first,
+        uint32_t n_units, uint32_t units_per_tile, uint32_t my_tiles, uint32_t n_static, unsigned int* __restrict__ tile_counter, uint32_t* __restrict__ g_h32, uint32_t part, uint32_t nparts, const __grid_constant__ FusedArgs fa)
 {
     extern __shared__ __align__(128) unsigned char smem[];
+#ifdef PHE_ENUM_PROF
+    if (fa.world > 0 && blockIdx.x == 0) PHE_ENUM_STAMP(fa.ws[fa.rank], 0);
+    PHE_ENUM_CTA_STAMP(0);
+#endif
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + kEnumHistOff);
     uint32_t* s_h9 = reinterpret_cast<uint32_t*>(smem + kEnumH9Off);   // per-CTA category counts fit 32 bits
     for (int i = threadIdx.x; i < kHistBinsPad; i += blockDim.x) s_hist[i] = 0;
@@ -381,37 +445,48 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
     }
     stage_image(smem, g_img, ENUM_IMG_BYTES, reinterpret_cast<uint64_t*>(smem + kEnumBarOff));
     __syncthreads();
+    PHE_ENUM_CTA_STAMP(1);
 
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t a_tri = sb + EOFF_TRI, a_ms = sb + EOFF_MSRANK, a_fl = sb + EOFF_FLUSH, a_hist = sb + kEnumHistOff;
     const uint32_t lane = threadIdx.x & 31;
     const Binom C{c_binom};
 
-    // Dynamic tile scheduling: tiles of `tile_size` consecutive colex indices are handed out through an atomic
-    // counter in increasing order.  Low indices hold the short blocks (small c3: few triples per block, poor lane
-    // use), i.e. the expensive tiles go first and the cheap ones level the finish line.
+    // Dynamic tile scheduling: a tile = `units_per_tile` consecutive work units of the colex axis (g_units: at most 512 hands
+    // or 4 enumeration blocks each, see build_enum_units), handed out through an atomic counter in increasing order.  Cutting
+    // by block count as well as by hands bounds the serial block set-ups one warp can be handed (runs of tiny blocks occur
+    // wherever c4 restarts), which is what kept single warps busy long after the rest of the launch had drained.
     const uint32_t a_bin = sb + kEnumBinOff;
-    for (;;) {
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(tile_counter, 1u);
-        tile = __shfl_sync(0xFFFFFFFFu, tile, 0) * nparts + part;   // this launch owns tiles == part (mod nparts)
-        if (tile >= ntiles) break;
-        // graded tiles: tile t holds 64 + 4t hands until that reaches tile_size (the first, expensive hands are
-        // cut fine so that no single warp sits on a long serial tile), then tile_size hands each
-        const uint32_t t0 = (tile_size - 64u) >> 2;
-        uint64_t wb, we;
-        if (tile < t0) {
-            wb = begin + 64ull * tile + 2ull * tile * (tile - 1u + (tile == 0u));
-            we = wb + 64u + 4u * tile;
-        } else {
-            wb = begin + 64ull * t0 + 2ull * t0 * (t0 - 1u + (t0 == 0u)) + (uint64_t)(tile - t0) * tile_size;
-            we = wb + tile_size;
+    // A launch owns the tiles == part (mod nparts); its j-th tile goes to warp j (mod W) for j < n_static (no atomic, W = warps
+    // of the grid: up to six rounds), the rest through the counter.  One 4736-way contended counter for EVERY tile was the
+    // limiter of short launches (a sharded part hands out 1.4 tiles/ns from one address, and each claim is a serial L2 round
+    // trip in front of the tile); tiles cost about the same by construction, and the dynamic rest evens out the finish line.
+    const uint32_t n_warps = gridDim.x * (kCtaThreads / 32);
+    uint32_t j = blockIdx.x * (kCtaThreads / 32) + (threadIdx.x >> 5);
+    bool dynamic = false;
+    for (;; j += n_warps) {
+        if (!dynamic && j >= n_static) dynamic = true;
+        if (dynamic) {
+            uint32_t got = 0;
+            if (lane == 0) got = atomicAdd(tile_counter, 1u);
+            j = n_static + __shfl_sync(0xFFFFFFFFu, got, 0);
         }
-        if (wb >= end) break;
-        if (we > end) we = end;
-        // warp-cooperative colex unrank: lane v (and v + 32) tests C(v, k) <= rem; the count of hits - 1 is c_i
-        int c[7];
-        {
+        if (j >= my_tiles) break;
+        const uint32_t tile = j * nparts + part;
+        const uint32_t u0 = tile * units_per_tile;
+        const uint32_t u1 = min(u0 + units_per_tile, n_units);
+        uint64_t wb = __ldg(g_units + unit_first + u0), we = __ldg(g_units + unit_first + u1);
+        const uint64_t packed = __ldg(g_unit_starts + unit_first + u0);
+        if (we > end) we = end;                                      // the last unit of a sub-range is clipped
+        int c3, c4, c5, c6;
+        uint32_t t_start;
+        if (wb >= begin) {                                           // the table knows where the unit starts
+            c3 = (int)(packed & 63u); c4 = (int)((packed >> 6) & 63u); c5 = (int)((packed >> 12) & 63u); c6 = (int)((packed >> 18) & 63u);
+            t_start = (uint32_t)(packed >> 24);
+        } else {                                                     // first unit of a sub-range that begins inside it
+            wb = begin;
+            // warp-cooperative colex unrank: lane v (and v + 32) tests C(v, k) <= rem; the count of hits - 1 is c_i
+            int c[7];
             uint32_t rem = (uint32_t)wb;
 #pragma unroll
             for (int i = 6; i >= 0; i--) {
@@ -421,10 +496,11 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
                 c[i] = hits - 1;
                 rem -= lds_u32(a_bin + 4u * ((uint32_t)(i + 1) * 64u + (uint32_t)c[i]));
             }
+            c3 = c[3]; c4 = c[4]; c5 = c[5]; c6 = c[6];
+            t_start = C(c[2], 3) + C(c[1], 2) + (uint32_t)c[0];
         }
-        int c3 = c[3], c4 = c[4], c5 = c[5], c6 = c[6];
+        if (wb >= we) continue;
         uint64_t remaining = we - wb;
-        uint32_t t_start = C(c[2], 3) + C(c[1], 2) + (uint32_t)c[0];
         for (;;) {
             EnumBlock b;
             enum_block_setup(c3, c4, c5, c6, C, b);
@@ -478,35 +554,62 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
         }
     }
     __syncthreads();
-    // flush: every CTA starts at a different bin so the 64-bit REDs do not pile up on one L2 line
-    const int rot = (int)((blockIdx.x * 397u) % (uint32_t)kHistBins);
-    for (int k = threadIdx.x; k < kHistBins; k += blockDim.x) {
-        int i = k + rot;
-        if (i >= kHistBins) i -= kHistBins;
-        const uint32_t v = s_hist[i];
-        if (v) {
-            if (hist7463) atomicAdd(hist7463 + i, (unsigned long long)v);
-            if (hist9) atomicAdd(s_h9 + category_of(i), v);   // native 32-bit shared atomic (the 64-bit form is a CAS loop)
+    PHE_ENUM_CTA_STAMP(2);
+    __shared__ uint32_t s_last;
+    if (fa.world > 0) {
+        // fused mode: one TMA bulk reduction of the whole shared histogram into the launch's u32 array (adds done by the L2)
+        if (threadIdx.x == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the shared atomics above -> visible to the TMA read
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u32 [%0], [%1], %2;" ::"l"(g_h32), "r"(a_hist), "r"((uint32_t)(kHistBinsPad * 4))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // reads AND global adds of the group complete
+            asm volatile("fence.proxy.async;" ::: "memory");
         }
+    } else {
+        // plain mode: every CTA starts at a different bin so the 64-bit REDs do not pile up on one L2 line.  Category counts:
+        // bins are ordered by category, so the 32 consecutive bins of a warp nearly always share one -> a warp reduction
+        // and ONE shared atomic (32 lanes adding to the same shared word serialise)
+        const int rot = (int)((blockIdx.x * 397u) % (uint32_t)kHistBins);
+        for (int k0 = 0; k0 < kHistBins; k0 += blockDim.x) {           // whole warps iterate: the reduction is warp-wide
+            const int k = k0 + threadIdx.x;
+            int i = k + rot;
+            if (i >= kHistBins) i -= kHistBins;
+            const uint32_t v = k < kHistBins ? s_hist[i] : 0u;
+            if (v && hist7463) atomicAdd(hist7463 + i, (unsigned long long)v);
+            if (hist9) {
+                const int cat = category_of((uint32_t)min(i, kHistBins - 1));
+                const int c_first = __shfl_sync(0xFFFFFFFFu, cat, 0);
+                if (__all_sync(0xFFFFFFFFu, cat == c_first || v == 0u)) {
+                    const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, v);   // per-CTA counts fit 32 bits
+                    if (lane == 0 && tot) atomicAdd(s_h9 + c_first, tot);
+                } else if (v) atomicAdd(s_h9 + cat, v);                 // native 32-bit shared atomic (the 64-bit form is a CAS loop)
+            }
+        }
+        __syncthreads();
+        if (hist9 && threadIdx.x < 9 && s_h9[threadIdx.x]) atomicAdd(hist9 + threadIdx.x, (unsigned long long)s_h9[threadIdx.x]);
+        __threadfence();
+        __syncthreads();
     }
-    __syncthreads();
-    if (hist9 && threadIdx.x < 9 && s_h9[threadIdx.x]) atomicAdd(hist9 + threadIdx.x, (unsigned long long)s_h9[threadIdx.x]);
+    PHE_ENUM_CTA_STAMP(3);
     // completion ticket: the last CTA re-arms the tile counter for the next launch (no memset node in front of the
     // kernel) and, in fused mode, owns the all-reduce
-    __shared__ uint32_t s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(tile_counter + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
-    __syncthreads();
-    if (s_last) {
-        if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const bool last = atomicAdd(tile_counter + 1, 1u) == gridDim.x - 1;
+        if (last) {
             tile_counter[0] = 0;
             tile_counter[1] = 0;
+            __threadfence();                                              // acquire side: the other CTAs' flushes, for the whole CTA via the barrier
+            asm volatile("fence.proxy.async;" ::: "memory");
         }
-        if (fa.world > 0) {
-            __threadfence();
-            enum_allreduce_epilogue(fa);
-        }
+        s_last = last ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last && fa.world > 0) {
+        if (threadIdx.x < 9) s_h9[threadIdx.x] = 0;
+        __syncthreads();
+        enum_allreduce_epilogue(fa, g_h32, s_h9);
     }
 }
 
@@ -1153,6 +1256,7 @@ namespace {
 
 constexpr int kMaxDevices = 64;
 constexpr uint32_t kCounterRing = 256;
+constexpr uint32_t kEnumRing = 64;      // per-launch u32 histograms of the enumeration (30 KB each), one per in-flight launch
 
 struct DevCtx {
     std::once_flag once;
@@ -1160,8 +1264,11 @@ struct DevCtx {
     uint16_t* d_image = nullptr;
     unsigned char* d_enum = nullptr;
     uint64_t* d_trimask = nullptr;
+    uint32_t* d_units = nullptr;          // work-unit boundaries of the enumeration (build_enum_units)
+    uint64_t* d_unit_starts = nullptr;    // packed block / triple at which every unit starts
     uint64_t* d_pairmask = nullptr;
     unsigned int* d_counters = nullptr;   // ring of {tile counter, completion ticket} pairs, one per in-flight enumeration launch
+    uint32_t* d_h32 = nullptr;            // ring of u32[kHistBinsPad] flush targets of k_enum7 (zero at rest, cleared by the kernel's last CTA)
     std::atomic<uint32_t> next_counter{0};
     int sm_count = 0;
 };
@@ -1174,6 +1281,9 @@ std::once_flag g_image_once;
 std::vector<uint16_t> g_image;
 std::vector<unsigned char> g_enum_image;
 std::vector<uint64_t> g_trimask;
+std::vector<uint32_t> g_enum_units;
+std::vector<uint64_t> g_enum_unit_starts;
+constexpr uint32_t kEnumUnitHands = 512, kEnumUnitBlocks = 4;
 HashParams g_hp;
 uint32_t g_binom[53 * 8];
 bool g_image_ok = false;
@@ -1199,6 +1309,7 @@ void init_device(int device)
         g_enum_image.resize(ENUM_IMG_BYTES);
         g_trimask.resize(N_TRIPLES);
         g_image_ok = g_image_ok && build_enum_image(g_enum_image.data(), g_trimask.data());
+        build_enum_units(g_enum_units, g_enum_unit_starts, kEnumUnitHands, kEnumUnitBlocks);
         build_binom(g_binom);
     });
     if (!g_image_ok) { cx.status = PHE_EINVAL; return; }
@@ -1222,8 +1333,14 @@ void init_device(int device)
     chk(cudaMemcpy(cx.d_enum, g_enum_image.data(), ENUM_IMG_BYTES, cudaMemcpyHostToDevice), "cudaMemcpy(enum tables)");
     chk(cudaMalloc(&cx.d_trimask, TRIMASK_BYTES), "cudaMalloc(trimask)");
     chk(cudaMemcpy(cx.d_trimask, g_trimask.data(), TRIMASK_BYTES, cudaMemcpyHostToDevice), "cudaMemcpy(trimask)");
+    chk(cudaMalloc(&cx.d_units, g_enum_units.size() * sizeof(uint32_t)), "cudaMalloc(enum units)");
+    chk(cudaMemcpy(cx.d_units, g_enum_units.data(), g_enum_units.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "cudaMemcpy(enum units)");
+    chk(cudaMalloc(&cx.d_unit_starts, g_enum_unit_starts.size() * sizeof(uint64_t)), "cudaMalloc(enum unit starts)");
+    chk(cudaMemcpy(cx.d_unit_starts, g_enum_unit_starts.data(), g_enum_unit_starts.size() * sizeof(uint64_t), cudaMemcpyHostToDevice), "cudaMemcpy(enum unit starts)");
     chk(cudaMalloc(&cx.d_counters, 2 * kCounterRing * sizeof(unsigned int)), "cudaMalloc(counters)");
     chk(cudaMemset(cx.d_counters, 0, 2 * kCounterRing * sizeof(unsigned int)), "cudaMemset(counters)");
+    chk(cudaMalloc(&cx.d_h32, (size_t)kEnumRing * kHistBinsPad * sizeof(uint32_t)), "cudaMalloc(h32)");
+    chk(cudaMemset(cx.d_h32, 0, (size_t)kEnumRing * kHistBinsPad * sizeof(uint32_t)), "cudaMemset(h32)");
     {
         std::vector<uint64_t> pm(DEALTAB_ENTRIES);   // pairs, then singles; the plan fast path reads the pair prefix
         build_dealtab(pm.data());
@@ -1432,23 +1549,22 @@ static int launch_enum7(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin
     int rc = current_ctx(&cx);
     if (rc) return rc;
     const uint64_t total = comb_end - comb_begin;
-    // the tiling depends only on (range, nparts): about 8 tiles per resident warp of one part, but never fewer than
-    // 512 hands (per-tile unranking and partial blocks) nor more than 2048 (tail balance)
-    uint64_t tile = total / ((uint64_t)nparts * cx->sm_count * (kCtaThreads / 32) * 8);
-    if (tile < 512) tile = 512;
-#ifndef PHE_ENUM_TILE_MAX
-#define PHE_ENUM_TILE_MAX 2048
-#endif
-    if (tile > PHE_ENUM_TILE_MAX) tile = PHE_ENUM_TILE_MAX;
-    tile &= ~(uint64_t)3;
-    // graded tiling (see k_enum7): sizes 64, 68, 72, ... up to `tile`, then constant
-    const uint64_t t0 = (tile - 64) / 4, s0 = 64 * t0 + (t0 ? 2 * t0 * (t0 - 1) : 0);
-    uint64_t ntiles;
-    if (total >= s0) ntiles = t0 + (total - s0 + tile - 1) / tile;
-    else {
-        ntiles = 0;
-        for (uint64_t covered = 0; covered < total; ntiles++) covered += 64 + 4 * ntiles;
+    // work units [unit_first, unit_first + n_units) of the static unit table overlap the range; a tile is 1..4 of them: about
+    // 8 tiles per resident warp of one part, but never more than 4 units (2048 hands: tail balance)
+    const std::vector<uint32_t>& units = g_enum_units;
+    uint64_t unit_first = 0, n_units = 0;
+    if (total) {
+        unit_first = (uint64_t)(std::upper_bound(units.begin(), units.end(), (uint32_t)comb_begin) - units.begin()) - 1;
+        const uint64_t unit_last = (uint64_t)(std::lower_bound(units.begin(), units.end(), (uint32_t)comb_end) - units.begin()) - 1;
+        n_units = unit_last - unit_first + 1;
     }
+    uint64_t per_tile = total / ((uint64_t)nparts * cx->sm_count * (kCtaThreads / 32) * 8) / kEnumUnitHands;
+    if (per_tile < 1) per_tile = 1;
+#ifndef PHE_ENUM_TILE_UNITS
+#define PHE_ENUM_TILE_UNITS 4
+#endif
+    if (per_tile > PHE_ENUM_TILE_UNITS) per_tile = PHE_ENUM_TILE_UNITS;
+    const uint64_t ntiles = (n_units + per_tile - 1) / per_tile;
     const uint64_t mine = ntiles > part ? (ntiles - part + nparts - 1) / nparts : 0;
     if (mine == 0 && fa.world == 0) return PHE_OK;
     uint64_t ctas = (mine + kCtaThreads / 32 - 1) / (kCtaThreads / 32);
@@ -1456,10 +1572,19 @@ static int launch_enum7(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin
     if (ctas > (uint64_t)cx->sm_count) ctas = cx->sm_count;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // {tile counter, completion ticket}: zero at rest, re-armed by the kernel's last CTA
-    unsigned int* counter = cx->d_counters + 2 * (cx->next_counter.fetch_add(1, std::memory_order_relaxed) % kCounterRing);
+    const uint32_t seq = cx->next_counter.fetch_add(1, std::memory_order_relaxed);
+    unsigned int* counter = cx->d_counters + 2 * (seq % kCounterRing);
+    uint32_t* h32 = cx->d_h32 + (size_t)(seq % kEnumRing) * kHistBinsPad;
+    // static share of this part's tiles: whole rounds over the grid's warps, at most 7/8 of the tiles and at most
+    // kStaticRoundsMax rounds (work pinned to a warp cannot be levelled afterwards, so long launches stay mostly dynamic)
+    const uint64_t n_warps = ctas * (kCtaThreads / 32);
+    uint64_t rounds = (mine - (mine >> 3)) / n_warps;
+    constexpr uint64_t kStaticRoundsMax = 6;   // swept 0..8 on a B200: 6 is best or tied for the whole range, halves and eighths
+    if (rounds > kStaticRoundsMax) rounds = kStaticRoundsMax;
+    const uint64_t n_static = rounds * n_warps;
     k_enum7<<<(unsigned)ctas, kCtaThreads, kSmemEnum, st>>>(
         cx->d_enum, cx->d_trimask, reinterpret_cast<unsigned long long*>(hist9), reinterpret_cast<unsigned long long*>(hist7463), comb_begin, comb_end,
-        (uint32_t)tile, (uint32_t)ntiles, counter, part, nparts, fa);
+        cx->d_units, cx->d_unit_starts, (uint32_t)unit_first, (uint32_t)n_units, (uint32_t)per_tile, (uint32_t)mine, (uint32_t)n_static, counter, h32, part, nparts, fa);
     return after_launch("enum7 launch");
 }
 
@@ -1471,6 +1596,15 @@ int phe_enum7_part(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin, uin
 }
 
 uint64_t phe_enum7_allreduce_workspace(void) { return kWsBytes; }
+
+#ifdef PHE_ENUM_PROF
+extern "C" int phe_debug_enum_prof(unsigned long long* host_out_1024)   // lab builds only (tools/lab/enum_stamps.py)
+{
+    PHE_CUDA(cudaDeviceSynchronize());
+    PHE_CUDA(cudaMemcpyFromSymbol(host_out_1024, g_enum_prof, sizeof(unsigned long long) * 1024));
+    return PHE_OK;
+}
+#endif
 
 int phe_enum7_allreduce(uint64_t* out_hist7472, uint64_t comb_begin, uint64_t comb_end, int rank, int world, void* const* peer_ws,
                         void* stream)
@@ -1484,8 +1618,7 @@ int phe_enum7_allreduce(uint64_t* out_hist7472, uint64_t comb_begin, uint64_t co
         fa.ws[r] = static_cast<unsigned char*>(peer_ws[r]);
     }
     fa.out = reinterpret_cast<unsigned long long*>(out_hist7472);
-    auto* acc = reinterpret_cast<uint64_t*>(fa.ws[rank] + kWsAcc);
-    return launch_enum7(acc, acc + 9, comb_begin, comb_end, (uint32_t)rank, (uint32_t)world, fa, stream);
+    return launch_enum7(nullptr, nullptr, comb_begin, comb_end, (uint32_t)rank, (uint32_t)world, fa, stream);
 }
 
 int phe_enum7_allreduce_status(const void* my_ws, void* stream, uint32_t* launches_out, uint32_t* failed_launch_out)

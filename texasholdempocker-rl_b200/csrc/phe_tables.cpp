@@ -304,4 +304,49 @@ bool build_enum_image(unsigned char* image, uint64_t* trimask)
     return true;
 }
 
+void build_enum_units(std::vector<uint32_t>& out, std::vector<uint64_t>& starts, uint32_t max_hands, uint32_t max_blocks)
+{
+    out.clear();
+    out.push_back(0);
+    uint32_t unit_start = 0, blocks_in = 0, pos = 0;
+    for (int c6 = 6; c6 < 52; c6++)
+        for (int c5 = 5; c5 < c6; c5++)
+            for (int c4 = 4; c4 < c5; c4++)
+                for (int c3 = 3; c3 < c4; c3++) {
+                    const uint32_t block_end = pos + binom_u32(c3, 3);
+                    for (;;) {
+                        const uint32_t room = max_hands - (pos - unit_start);
+                        if (block_end - pos >= room) {            // the unit fills up inside (or exactly at the end of) this block
+                            pos += room;
+                            out.push_back(pos);
+                            unit_start = pos;
+                            blocks_in = 0;
+                            if (pos == block_end) break;
+                        } else {                                  // the block ends inside the unit
+                            pos = block_end;
+                            if (++blocks_in >= max_blocks) {
+                                out.push_back(pos);
+                                unit_start = pos;
+                                blocks_in = 0;
+                            }
+                            break;
+                        }
+                    }
+                }
+    if (out.back() != pos) out.push_back(pos);
+    // second walk: the block and the triple offset at which every unit starts
+    starts.assign(out.size(), 0);
+    size_t u = 0;
+    uint32_t block_start = 0;
+    for (int c6 = 6; c6 < 52; c6++)
+        for (int c5 = 5; c5 < c6; c5++)
+            for (int c4 = 4; c4 < c5; c4++)
+                for (int c3 = 3; c3 < c4; c3++) {
+                    const uint32_t block_end = block_start + binom_u32(c3, 3);
+                    for (; u + 1 < out.size() && out[u] < block_end; u++)
+                        starts[u] = (uint64_t)c3 | (uint64_t)c4 << 6 | (uint64_t)c5 << 12 | (uint64_t)c6 << 18 | (uint64_t)(out[u] - block_start) << 24;
+                    block_start = block_end;
+                }
+}
+
 }  // namespace phe

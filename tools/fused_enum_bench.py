@@ -69,6 +69,12 @@ g2 = torch.cuda.CUDAGraph()
 with torch.cuda.graph(g2):
     nccl_step()
 t_nccl = timed(g2.replay)
+# a library built with -DPHE_ENUM_PROF leaves %globaltimer stamps of the last launch behind the status words
+nbytes = int(phe._native.lib().phe_enum7_allreduce_workspace())
+st = fe.ws[nbytes - 128 + 16: nbytes - 128 + 16 + 40].view(torch.int64).cpu().tolist()
+if st[0]:
+    names = ["enumerate+flush (CTA 0 start -> last CTA)", "push payload to peers", "signal + wait for peers", "sum slots"]
+    print(f"rank {rank}: " + ", ".join(f"{n} {(st[i + 1] - st[i]) / 1e3:.1f} us" for i, n in enumerate(names)), flush=True)
 if rank == 0:
     print(f"world {world}: fused {t_fused:.1f} us/step ({133784560/t_fused*1e6:.3e} evals/s)   kernel+NCCL {t_nccl:.1f} us/step")
 if world > 1:
