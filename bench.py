@@ -449,7 +449,7 @@ def main():
             e2e = {"value": NUM_HANDS / e2e_dt, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": (9 + 7463) * 8, "ms_per_step": e2e_dt * 1e3,
                    "api": "phe.enumerate_c52_7() -> phe_enum7_host: memset + kernel + D2H of both histograms; the workload has no input buffer"}
         out = {"value": NUM_HANDS * steps / (total_ms * 1e-3), "unit": "evals/s", "ms_per_step": total_ms / steps, "kern_ms": kern_ms, "e2e": e2e,
-               "collective": None if world == 1 else ("fused into k_enum7: peer-memory exchange by the last CTAs (phe_enum7_allreduce)" if fused is not None
+               "collective": None if world == 1 else (("fused into k_enum7: last CTA exchanges the 30 KB u32 histogram, " + ("NVLS multimem.red.add + multimem.st flag (phe_enum7_allreduce_nvls)" if fused.nvls else "peer stores + release flags (phe_enum7_allreduce)")) if fused is not None
                                                       else "NCCL all_reduce(int64[7472])"),
                "hands_this_rank": NUM_HANDS // world}
         del graph

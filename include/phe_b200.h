@@ -87,10 +87,11 @@ int phe_enum7_part(uint64_t *hist9, uint64_t *hist7463, uint64_t comb_begin, uin
                    uint32_t part, uint32_t nparts, void *stream);
 
 /* Fused enumeration + all-reduce over peer memory (one kernel per GPU, no separate collective).  Rank `rank` of
- * `world` (<= 8) enumerates its interleaved part of the range; the last CTA to finish pushes the rank's reduced
- * 7472-bin histogram (9 category bins followed by the 7463 rank bins) into its slot of EVERY rank's workspace with
- * peer stores over NVLink, raises a system-scope flag on each peer, waits for all peers' flags and sums the slots into
- * out_hist7472 (device pointer, local).  peer_ws[r] is rank r's workspace (device pointer valid in this process:
+ * `world` (<= 8) enumerates its interleaved part of the range; every CTA adds its histogram into a per-launch u32
+ * array with one TMA bulk reduction, and the last CTA to finish pushes that 30 KB array (a whole C(52,7) bin fits
+ * 32 bits) into its slot of EVERY rank's workspace with peer stores over NVLink, raises a system-scope flag on each
+ * peer, waits for all peers' flags and sums the slots into out_hist7472 (device pointer, local: 9 category bins followed
+ * by the 7463 rank bins, uint64).  peer_ws[r] is rank r's workspace (device pointer valid in this process:
  * CUDA IPC / torch symmetric memory), each phe_enum7_allreduce_workspace() bytes, zeroed once before first use.
  * The launch count (epoch) lives in the workspace, so the call may be captured in a CUDA graph and replayed; all
  * ranks must issue the same sequence of calls.  A peer that does not show up within ~2 s does not hang the kernel: the
@@ -100,6 +101,12 @@ int phe_enum7_part(uint64_t *hist9, uint64_t *hist7463, uint64_t comb_begin, uin
 uint64_t phe_enum7_allreduce_workspace(void);
 int phe_enum7_allreduce(uint64_t *out_hist7472, uint64_t comb_begin, uint64_t comb_end, int rank, int world,
                         void *const *peer_ws, void *stream);
+/* The same through NVLink SHARP (NVLS): multicast_ws is the MULTICAST mapping of the ranks' workspaces (CUDA multicast
+ * object / torch symmetric memory `multicast_ptr`).  Each rank adds its payload with multimem.red.add -- the switch
+ * applies one reduction to every rank's copy, so nothing is stored `world` times and no slots are summed -- and signals
+ * every rank with ONE multimem.st.  multicast_ws == NULL is phe_enum7_allreduce.  All ranks must use the same variant. */
+int phe_enum7_allreduce_nvls(uint64_t *out_hist7472, uint64_t comb_begin, uint64_t comb_end, int rank, int world,
+                             void *const *peer_ws, void *multicast_ws, void *stream);
 int phe_enum7_allreduce_status(const void *my_ws, void *stream, uint32_t *launches_out, uint32_t *failed_launch_out);
 
 /* ---- Monte-Carlo equity ------------------------------------------------- */

@@ -20,7 +20,7 @@ NUM_HANDS_7 = 133784560
 # every symbol include/phe_b200.h declares
 SYMBOLS = [
     "phe_strerror", "phe_last_cuda_error", "phe_version", "phe_init",
-    "phe_eval7", "phe_eval7_host", "phe_enum7", "phe_enum7_host", "phe_enum7_part", "phe_enum7_allreduce_workspace", "phe_enum7_allreduce", "phe_enum7_allreduce_status",
+    "phe_eval7", "phe_eval7_host", "phe_enum7", "phe_enum7_host", "phe_enum7_part", "phe_enum7_allreduce_workspace", "phe_enum7_allreduce", "phe_enum7_allreduce_nvls", "phe_enum7_allreduce_status",
     "phe_equity_mc", "phe_equity_mc_host", "phe_equity_plan", "phe_equity_plan_host", "phe_plan_num_deals",
     "phe_showdown", "phe_showdown_host", "phe_deal", "phe_deal_host", "phe_deal_samples", "phe_deal_samples_host", "phe_settle", "phe_settle_host", "phe_launch_count",
     "phe_nn_add_layernorm", "phe_nn_embed_obs", "phe_nn_attention", "phe_nn_policy_value_heads", "phe_obs_num_fields", "phe_obs_cut_table_bytes", "phe_encode_obs",
@@ -55,6 +55,7 @@ def lib():
     L.phe_enum7_part.argtypes = [vp, vp, u64, u64, u32, u32, vp]; L.phe_enum7_part.restype = i32
     L.phe_enum7_allreduce_workspace.argtypes = []; L.phe_enum7_allreduce_workspace.restype = u64
     L.phe_enum7_allreduce.argtypes = [vp, u64, u64, i32, i32, vp, vp]; L.phe_enum7_allreduce.restype = i32
+    L.phe_enum7_allreduce_nvls.argtypes = [vp, u64, u64, i32, i32, vp, vp, vp]; L.phe_enum7_allreduce_nvls.restype = i32
     L.phe_enum7_allreduce_status.argtypes = [vp, vp, vp, vp]; L.phe_enum7_allreduce_status.restype = i32
     L.phe_equity_mc.argtypes = [vp, i64, i32, u64, u64, u64, u32, vp, vp]; L.phe_equity_mc.restype = i32
     L.phe_equity_mc_host.argtypes = [vp, i64, i32, u64, u64, u64, u32, vp]; L.phe_equity_mc_host.restype = i32

@@ -280,7 +280,9 @@ __device__ __forceinline__ uint32_t enum_flush_addr(uint32_t x, uint32_t t, uint
 //
 // Workspace of one rank (all ranks use the same layout; peers write into it through NVLink):
 //   slots  u32[2][8][7464]   payload (bins, one pad word) of source rank s for launches of parity p
-//   flags  u32[8]            flags[s] = number of the last launch whose slot from rank s is complete
+//   flags  u32[8]            flags[s] = number of the last launch whose contribution from rank s is complete
+//   acc    u32[2][7464]      NVLS mode only: the sum itself, by launch parity (every rank multimem.red-adds its payload into
+//                            the multicast mapping of this array, i.e. into all ranks' copies at once; no slots are used)
 //   epoch  u32, failed u32   launch number (starts at 0 -> first launch is 1); launch number of a timed-out exchange
 constexpr int kAllBins = 9 + kHistBins;                       // 7472 (layout of the u64 result: hist9 then hist7463)
 static_assert(kAllBins == 7472, "phe_enum7_allreduce writes out_hist7472");
@@ -288,14 +290,16 @@ constexpr int kMaxWorld = 8;
 constexpr int kSlotWords = kHistBinsPad;                      // 7464 u32 = 1866 uint4
 constexpr size_t kWsSlots = 0;
 constexpr size_t kWsFlags = kWsSlots + (size_t)2 * kMaxWorld * kSlotWords * 4;
-constexpr size_t kWsEpoch = kWsFlags + 64;
+constexpr size_t kWsAcc = kWsFlags + 64;
+constexpr size_t kWsEpoch = kWsAcc + (size_t)2 * kSlotWords * 4;
 constexpr size_t kWsBytes = kWsEpoch + 128;                   // epoch, failed, then (PHE_ENUM_PROF) eight %globaltimer stamps
-static_assert(kSlotWords % 4 == 0 && kWsFlags % 16 == 0, "uint4 access to the slots");
+static_assert(kSlotWords % 4 == 0 && kWsFlags % 16 == 0 && kWsAcc % 16 == 0, "uint4 access to the slots");
 
 struct FusedArgs {
     int rank, world;                       // world == 0: plain kernel, results go to hist9 / hist7463
     unsigned char* ws[kMaxWorld];          // every rank's workspace
     unsigned long long* out;               // local all-reduced histogram [7472]
+    unsigned char* mc;                     // NVLS: multicast mapping of the workspaces (one store / reduction reaches every rank), or null
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -304,6 +308,14 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void multimem_red_add_u32(void* mc_addr, uint32_t v)
+{
+    asm volatile("multimem.red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(mc_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_st_release_u32(void* mc_addr, uint32_t v)
+{
+    asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(mc_addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {
@@ -336,7 +348,15 @@ __device__ __noinline__ void enum_allreduce_epilogue(const FusedArgs& fa, uint32
     const int world = fa.world;
     unsigned long long* const out = fa.out;
     PHE_ENUM_STAMP(my, 1);
-    // 1. payload -> slot (e, rank) of every rank; g_h32 cleared for the next launch.  Loads first, then the stores.
+    // 1. payload -> every rank; g_h32 cleared for the next launch.  Loads first, then the stores.
+    //    Peer-store mode: into slot (e, rank) of every rank's workspace.  NVLS mode: multimem.red.add into the multicast
+    //    mapping of acc[e & 1] -- the switch delivers the addition to all ranks' copies, so one reduction per non-zero bin
+    //    replaces `world` stores and nobody has to sum slots afterwards; acc[(e + 1) & 1] of THIS rank is cleared here,
+    //    before the signal: peers add to it only in launch e + 1, which they start after they have seen this launch's flag.
+    //    (Also tried: leaving the payload at home and pulling the sum with multimem.ld_reduce.add.u64 on bin pairs -- no push
+    //    at all, but the 3732 eight-byte reductions per rank take 9.4 us against 3.0 + 3.8 us for this push + local read.)
+    const bool nvls = fa.mc != nullptr;
+    const size_t acc_off = kWsAcc + (size_t)(e & 1u) * kSlotWords * 4;
     {
         uint4 v[kVecPer];
 #pragma unroll
@@ -344,13 +364,28 @@ __device__ __noinline__ void enum_allreduce_epilogue(const FusedArgs& fa, uint32
             const int g = threadIdx.x + k * kCtaThreads;
             v[k] = g < kHistVec ? __ldcg(reinterpret_cast<const uint4*>(g_h32) + g) : make_uint4(0, 0, 0, 0);
         }
-#pragma unroll 1   // once-per-launch code runs from a cold instruction cache: compact beats unrolled here
-        for (int p = 0; p < world; p++) {
-            uint4* dst = reinterpret_cast<uint4*>(fa.ws[p] + slot_off);
+        if (nvls) {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(fa.mc + acc_off);
+            uint4* next = reinterpret_cast<uint4*>(my + kWsAcc + (size_t)((e + 1u) & 1u) * kSlotWords * 4);
 #pragma unroll
             for (int k = 0; k < kVecPer; k++) {
                 const int g = threadIdx.x + k * kCtaThreads;
-                if (g < kHistVec) dst[g] = v[k];
+                if (g >= kHistVec) continue;
+                if (v[k].x) multimem_red_add_u32(dst + 4 * g + 0, v[k].x);
+                if (v[k].y) multimem_red_add_u32(dst + 4 * g + 1, v[k].y);
+                if (v[k].z) multimem_red_add_u32(dst + 4 * g + 2, v[k].z);
+                if (v[k].w) multimem_red_add_u32(dst + 4 * g + 3, v[k].w);
+                next[g] = make_uint4(0, 0, 0, 0);
+            }
+        } else {
+#pragma unroll 1   // once-per-launch code runs from a cold instruction cache: compact beats unrolled here
+            for (int p = 0; p < world; p++) {
+                uint4* dst = reinterpret_cast<uint4*>(fa.ws[p] + slot_off);
+#pragma unroll
+                for (int k = 0; k < kVecPer; k++) {
+                    const int g = threadIdx.x + k * kCtaThreads;
+                    if (g < kHistVec) dst[g] = v[k];
+                }
             }
         }
 #pragma unroll
@@ -363,7 +398,8 @@ __device__ __noinline__ void enum_allreduce_epilogue(const FusedArgs& fa, uint32
     PHE_ENUM_STAMP(my, 2);
     // 2. tell every rank that slot (e, rank) is complete; 3. wait until all of this rank's slots of launch e are
     if ((int)threadIdx.x < world) {
-        st_release_sys(reinterpret_cast<uint32_t*>(fa.ws[threadIdx.x] + kWsFlags) + fa.rank, e);
+        if (!nvls) st_release_sys(reinterpret_cast<uint32_t*>(fa.ws[threadIdx.x] + kWsFlags) + fa.rank, e);
+        else if (threadIdx.x == 0) multimem_st_release_u32(reinterpret_cast<uint32_t*>(fa.mc + kWsFlags) + fa.rank, e);   // one store, every rank's flags[rank]
         const uint32_t* mine = reinterpret_cast<const uint32_t*>(my + kWsFlags) + threadIdx.x;
         const long long t0 = clock64();
         bool ok = true;
@@ -380,12 +416,13 @@ __device__ __noinline__ void enum_allreduce_epilogue(const FusedArgs& fa, uint32
     // 4. sum the slots (all loads of a group in flight together), widen to the u64 result: hist9 at [0, 9), bins at [9, 7472).
     //    The nine category counts are segment sums of the summed bins: bins are ordered by category, so a warp's 128
     //    consecutive bins nearly always lie in one category -> one warp reduction and one shared atomic per warp.
-    const unsigned char* base = my + kWsSlots + (size_t)(e & 1u) * kMaxWorld * kSlotWords * 4;
+    const unsigned char* base = nvls ? my + acc_off : my + kWsSlots + (size_t)(e & 1u) * kMaxWorld * kSlotWords * 4;
+    const int n_slots = nvls ? 1 : world;                              // NVLS: acc already holds the sum of all ranks
     unsigned long long sum[kVecPer][4];
 #pragma unroll
     for (int k = 0; k < kVecPer; k++) sum[k][0] = sum[k][1] = sum[k][2] = sum[k][3] = 0;
-#pragma unroll 2
-    for (int s = 0; s < world; s++) {                                  // slot loop outside: the loads of both groups fly together
+#pragma unroll 4
+    for (int s = 0; s < n_slots; s++) {                                // slot loop outside: the loads of both groups fly together
         const uint4* slot = reinterpret_cast<const uint4*>(base + (size_t)s * kSlotWords * 4);
 #pragma unroll
         for (int k = 0; k < kVecPer; k++) {
@@ -1558,7 +1595,10 @@ static int launch_enum7(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin
         const uint64_t unit_last = (uint64_t)(std::lower_bound(units.begin(), units.end(), (uint32_t)comb_end) - units.begin()) - 1;
         n_units = unit_last - unit_first + 1;
     }
-    uint64_t per_tile = total / ((uint64_t)nparts * cx->sm_count * (kCtaThreads / 32) * 8) / kEnumUnitHands;
+#ifndef PHE_ENUM_TILES_PER_WARP
+#define PHE_ENUM_TILES_PER_WARP 8
+#endif
+    uint64_t per_tile = total / ((uint64_t)nparts * cx->sm_count * (kCtaThreads / 32) * PHE_ENUM_TILES_PER_WARP) / kEnumUnitHands;
     if (per_tile < 1) per_tile = 1;
 #ifndef PHE_ENUM_TILE_UNITS
 #define PHE_ENUM_TILE_UNITS 4
@@ -1606,8 +1646,8 @@ extern "C" int phe_debug_enum_prof(unsigned long long* host_out_1024)   // lab b
 }
 #endif
 
-int phe_enum7_allreduce(uint64_t* out_hist7472, uint64_t comb_begin, uint64_t comb_end, int rank, int world, void* const* peer_ws,
-                        void* stream)
+int phe_enum7_allreduce_nvls(uint64_t* out_hist7472, uint64_t comb_begin, uint64_t comb_end, int rank, int world, void* const* peer_ws,
+                             void* multicast_ws, void* stream)
 {
     if (!out_hist7472 || !peer_ws || world < 1 || world > kMaxWorld || rank < 0 || rank >= world) return PHE_EINVAL;
     FusedArgs fa{};
@@ -1618,7 +1658,14 @@ int phe_enum7_allreduce(uint64_t* out_hist7472, uint64_t comb_begin, uint64_t co
         fa.ws[r] = static_cast<unsigned char*>(peer_ws[r]);
     }
     fa.out = reinterpret_cast<unsigned long long*>(out_hist7472);
+    fa.mc = static_cast<unsigned char*>(multicast_ws);
     return launch_enum7(nullptr, nullptr, comb_begin, comb_end, (uint32_t)rank, (uint32_t)world, fa, stream);
+}
+
+int phe_enum7_allreduce(uint64_t* out_hist7472, uint64_t comb_begin, uint64_t comb_end, int rank, int world, void* const* peer_ws,
+                        void* stream)
+{
+    return phe_enum7_allreduce_nvls(out_hist7472, comb_begin, comb_end, rank, world, peer_ws, nullptr, stream);
 }
 
 int phe_enum7_allreduce_status(const void* my_ws, void* stream, uint32_t* launches_out, uint32_t* failed_launch_out)

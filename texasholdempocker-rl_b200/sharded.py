@@ -74,11 +74,15 @@ def sharded_enum7(group=None, local_fn=None, comb_begin=0, comb_end=N.NUM_HANDS_
 
 class FusedEnum7:
     """Exhaustive enumeration sharded over the ranks of `group` with the histogram all-reduce fused into the
-    enumeration kernel (phe_enum7_allreduce): the last CTA of each rank's kernel exchanges the 60 KB histogram through
-    peer memory over NVLink, so a step is ONE kernel per GPU and can be captured in a CUDA graph.  torch's symmetric
-    memory provides the peer-mapped workspace (plumbing only); with one rank no peer mapping is needed."""
+    enumeration kernel (phe_enum7_allreduce[_nvls]): the last CTA of each rank's kernel exchanges the 30 KB u32 histogram
+    through peer memory over NVLink, so a step is ONE kernel per GPU and can be captured in a CUDA graph.  torch's symmetric
+    memory provides the peer-mapped workspace (plumbing only); with one rank no peer mapping is needed.
 
-    def __init__(self, group=None):
+    nvls: None = use the NVLink-SHARP multicast mapping when symmetric memory offers one and the group has four ranks or more
+    (multimem.red.add: one reduction reaches every rank, one multimem.st signals them, no per-rank slots to sum; with two
+    ranks plain peer stores measure the same), True = require it, False = plain peer stores.  All ranks decide alike."""
+
+    def __init__(self, group=None, nvls=None):
         import ctypes as C
         self.rank, self.world = _world(group)
         L = N.lib()
@@ -90,9 +94,17 @@ class FusedEnum7:
             self.ws = symm.empty(nbytes, dtype=torch.uint8, device=dev)
             self.handle = symm.rendezvous(self.ws, g.group_name if hasattr(g, "group_name") else g)
             ptrs = [int(p) for p in self.handle.buffer_ptrs]
+            mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+            have = torch.tensor([1 if mc else 0], device=dev)
+            dist.all_reduce(have, op=dist.ReduceOp.MIN, group=group)          # every rank or none
+            if nvls is True and not int(have.item()):
+                raise N.PheError("FusedEnum7(nvls=True): symmetric memory has no multicast mapping on this system")
+            self._mc = mc if (int(have.item()) and (nvls is True or (nvls is None and self.world >= 4))) else 0
         else:
             self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             ptrs = [self.ws.data_ptr()]
+            self._mc = 0
+        self.nvls = bool(self._mc)
         self.ws.zero_()
         torch.cuda.synchronize()
         if self.world > 1:
@@ -103,8 +115,8 @@ class FusedEnum7:
     def run(self, comb_begin=0, comb_end=N.NUM_HANDS_7):
         """Launches on the current stream; returns views (hist9, hist7463) of the all-reduced result buffer."""
         import ctypes as C
-        N.check(N.lib().phe_enum7_allreduce(C.c_void_p(self.out.data_ptr()), comb_begin, comb_end, self.rank, self.world, self._ptrs,
-                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        N.check(N.lib().phe_enum7_allreduce_nvls(C.c_void_p(self.out.data_ptr()), comb_begin, comb_end, self.rank, self.world, self._ptrs,
+                                                 C.c_void_p(self._mc) if self._mc else None, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return self.out[:9], self.out[9:]
 
     def check(self):

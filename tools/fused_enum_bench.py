@@ -16,7 +16,8 @@ torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 gold = json.load(open(os.path.join(ROOT, "tests", "golden", "hist7463.json")))
-fe = phe.FusedEnum7()  # fe.check() at the end raises if a peer missed an exchange
+nvls = {None: None, '0': False, '1': True}[os.environ.get('PHE_FUSED_NVLS')]   # default: NVLS when the system offers a multicast mapping
+fe = phe.FusedEnum7(nvls=nvls)  # fe.check() at the end raises if a peer missed an exchange
 for it in range(5):
     h9, h = fe.run()
     torch.cuda.synchronize()
@@ -76,7 +77,7 @@ if st[0]:
     names = ["enumerate+flush (CTA 0 start -> last CTA)", "push payload to peers", "signal + wait for peers", "sum slots"]
     print(f"rank {rank}: " + ", ".join(f"{n} {(st[i + 1] - st[i]) / 1e3:.1f} us" for i, n in enumerate(names)), flush=True)
 if rank == 0:
-    print(f"world {world}: fused {t_fused:.1f} us/step ({133784560/t_fused*1e6:.3e} evals/s)   kernel+NCCL {t_nccl:.1f} us/step")
+    print(f"world {world} ({'NVLS multimem' if fe.nvls else 'peer stores'}): fused {t_fused:.1f} us/step ({133784560/t_fused*1e6:.3e} evals/s)   kernel+NCCL {t_nccl:.1f} us/step")
 if world > 1:
     del g, g2
     torch.cuda.synchronize(); dist.barrier(); sys.stdout.flush(); os._exit(0)
