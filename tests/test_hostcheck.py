@@ -143,11 +143,10 @@ def test_enum_work_units(hostcheck):
     assert n < 300000                                                  # ~1.1 MB + 2.2 MB tables
     # the packed start of every unit is the colex unranking of its first index
     st = starts[:n - 1].astype(np.int64)
-    c3, c4, c5, c6, tri = st & 63, (st >> 6) & 63, (st >> 12) & 63, (st >> 18) & 63, st >> 24
-    c4t = np.array([comb(v, 4) for v in range(53)]); c5t = np.array([comb(v, 5) for v in range(53)])
-    c6t = np.array([comb(v, 6) for v in range(53)]); c7t = np.array([comb(v, 7) for v in range(53)]); c3t = np.array([comb(v, 3) for v in range(53)])
-    assert (c3 < c4).all() and (c4 < c5).all() and (c5 < c6).all() and (c6 < 52).all() and (tri < c3t[c3]).all()
-    assert (tri + c4t[c3] + c5t[c4] + c6t[c5] + c7t[c6] == u[:-1]).all()
+    blk, tri = st & ((1 << 18) - 1), st >> 18
+    block_start = np.concatenate([[0], ends[:-1]])                     # block id = position in colex order of the (c3..c6) suffixes
+    assert blk.max() == len(sizes) - 1 == 211876 - 1 and (np.diff(blk) >= 0).all()
+    assert (tri < sizes[blk]).all() and (block_start[blk] + tri == u[:-1]).all()
 
 
 def test_multiply_shift_reductions_are_exact():

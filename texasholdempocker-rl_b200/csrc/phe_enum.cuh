@@ -25,6 +25,15 @@ constexpr uint32_t EOFF_TRI = EOFF_FLUSH + 16384;             // 117,168
 constexpr uint32_t ENUM_IMG_BYTES = EOFF_TRI + N_TRIPLES * 4; // 190,864 (multiple of 16)
 constexpr uint32_t TRIMASK_BYTES = N_TRIPLES * 8;
 
+constexpr uint32_t N_ENUM_BLOCKS = 211876;      // C(49,4): suffixes 3 <= c3 < c4 < c5 < c6 <= 51, id = colex rank of (c3-3, .., c6-3)
+
+// one enumeration block as the kernel reads it (16 bytes, table in global memory / L2; built from enum_block_setup)
+struct EnumBlockRec {
+    uint32_t s3lo, s3hi;   // card set of c3..c6
+    uint32_t idx_n;        // bidx3 (16 bits: < 50388) | ntriples << 16 (<= C(48,3) = 17296)
+    uint32_t kbias;
+};
+
 struct EnumBlock {
     uint64_t s3;        // card set of c3..c6
     uint32_t bidx3;     // sum_{i=4..7} C(r_i + i - 1, i)

@@ -463,7 +463,7 @@ __device__ __noinline__ void enum_allreduce_epilogue(const FusedArgs& fa, uint32
 
 __global__ void __launch_bounds__(kCtaThreads, 1)
 k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_trimask, unsigned long long* __restrict__ hist9,
-        unsigned long long* __restrict__ hist7463, uint64_t begin, uint64_t end, const uint32_t* __restrict__ g_units, const uint64_t* __restrict__ g_unit_starts, uint32_t unit_first,
+        unsigned long long* __restrict__ hist7463, uint64_t begin, uint64_t end, const uint32_t* __restrict__ g_units, const uint64_t* __restrict__ g_unit_starts, const uint4* __restrict__ g_blocks, uint32_t unit_first,
         uint32_t n_units, uint32_t units_per_tile, uint32_t my_tiles, uint32_t n_static, unsigned int* __restrict__ tile_counter, uint32_t* __restrict__ g_h32, uint32_t part, uint32_t nparts, const __grid_constant__ FusedArgs fa)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -515,11 +515,10 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
         uint64_t wb = __ldg(g_units + unit_first + u0), we = __ldg(g_units + unit_first + u1);
         const uint64_t packed = __ldg(g_unit_starts + unit_first + u0);
         if (we > end) we = end;                                      // the last unit of a sub-range is clipped
-        int c3, c4, c5, c6;
-        uint32_t t_start;
+        uint32_t blk, t_start;
         if (wb >= begin) {                                           // the table knows where the unit starts
-            c3 = (int)(packed & 63u); c4 = (int)((packed >> 6) & 63u); c5 = (int)((packed >> 12) & 63u); c6 = (int)((packed >> 18) & 63u);
-            t_start = (uint32_t)(packed >> 24);
+            blk = (uint32_t)packed & 0x3FFFFu;
+            t_start = (uint32_t)(packed >> 18);
         } else {                                                     // first unit of a sub-range that begins inside it
             wb = begin;
             // warp-cooperative colex unrank: lane v (and v + 32) tests C(v, k) <= rem; the count of hits - 1 is c_i
@@ -533,18 +532,21 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
                 c[i] = hits - 1;
                 rem -= lds_u32(a_bin + 4u * ((uint32_t)(i + 1) * 64u + (uint32_t)c[i]));
             }
-            c3 = c[3]; c4 = c[4]; c5 = c[5]; c6 = c[6];
+            blk = C(c[3] - 3, 1) + C(c[4] - 3, 2) + C(c[5] - 3, 3) + C(c[6] - 3, 4);   // colex rank of the shifted suffix
             t_start = C(c[2], 3) + C(c[1], 2) + (uint32_t)c[0];
         }
         if (wb >= we) continue;
         uint64_t remaining = we - wb;
+        // block records come from the L2-resident table (one 16-byte load instead of eight binomial look-ups and the
+        // suit arithmetic of enum_block_setup: block set-up was a fifth of all executed instructions); the next block's
+        // record is requested before this block's hands are processed
+        uint4 rec = __ldg(g_blocks + blk);
         for (;;) {
-            EnumBlock b;
-            enum_block_setup(c3, c4, c5, c6, C, b);
-            uint32_t stop = b.ntriples;
+            const uint4 rec_next = __ldg(g_blocks + min(blk + 1u, N_ENUM_BLOCKS - 1u));
+            uint32_t stop = rec.z >> 16;                              // ntriples
             if ((uint64_t)stop > (uint64_t)t_start + remaining) stop = (uint32_t)(t_start + remaining);
-            const uint32_t msb = a_ms + 2u * b.bidx3;
-            const uint32_t s3lo = (uint32_t)b.s3, s3hi = (uint32_t)(b.s3 >> 32), kbias = b.kbias;
+            const uint32_t msb = a_ms + 2u * (rec.z & 0xFFFFu);
+            const uint32_t s3lo = rec.x, s3hi = rec.y, kbias = rec.w;
             // warp-uniform trip counts; kU hands per lane per trip keep kU independent LDS -> (LDG) -> LDS -> ATOMS
             // chains in flight, which is what hides the L2 round trip of the flush path
 #ifndef PHE_ENUM_KU
@@ -587,7 +589,8 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
             remaining -= stop - t_start;
             if (!remaining) break;
             t_start = 0;
-            enum_block_next(c3, c4, c5, c6);
+            blk++;
+            rec = rec_next;
         }
     }
     __syncthreads();
@@ -1303,6 +1306,7 @@ struct DevCtx {
     uint64_t* d_trimask = nullptr;
     uint32_t* d_units = nullptr;          // work-unit boundaries of the enumeration (build_enum_units)
     uint64_t* d_unit_starts = nullptr;    // packed block / triple at which every unit starts
+    EnumBlockRec* d_blocks = nullptr;     // the 211,876 enumeration blocks as the kernel reads them (3.4 MB, L2 resident)
     uint64_t* d_pairmask = nullptr;
     unsigned int* d_counters = nullptr;   // ring of {tile counter, completion ticket} pairs, one per in-flight enumeration launch
     uint32_t* d_h32 = nullptr;            // ring of u32[kHistBinsPad] flush targets of k_enum7 (zero at rest, cleared by the kernel's last CTA)
@@ -1320,6 +1324,7 @@ std::vector<unsigned char> g_enum_image;
 std::vector<uint64_t> g_trimask;
 std::vector<uint32_t> g_enum_units;
 std::vector<uint64_t> g_enum_unit_starts;
+std::vector<EnumBlockRec> g_enum_blocks;
 constexpr uint32_t kEnumUnitHands = 512, kEnumUnitBlocks = 4;
 HashParams g_hp;
 uint32_t g_binom[53 * 8];
@@ -1347,6 +1352,7 @@ void init_device(int device)
         g_trimask.resize(N_TRIPLES);
         g_image_ok = g_image_ok && build_enum_image(g_enum_image.data(), g_trimask.data());
         build_enum_units(g_enum_units, g_enum_unit_starts, kEnumUnitHands, kEnumUnitBlocks);
+        build_enum_blocks(g_enum_blocks);
         build_binom(g_binom);
     });
     if (!g_image_ok) { cx.status = PHE_EINVAL; return; }
@@ -1374,6 +1380,8 @@ void init_device(int device)
     chk(cudaMemcpy(cx.d_units, g_enum_units.data(), g_enum_units.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "cudaMemcpy(enum units)");
     chk(cudaMalloc(&cx.d_unit_starts, g_enum_unit_starts.size() * sizeof(uint64_t)), "cudaMalloc(enum unit starts)");
     chk(cudaMemcpy(cx.d_unit_starts, g_enum_unit_starts.data(), g_enum_unit_starts.size() * sizeof(uint64_t), cudaMemcpyHostToDevice), "cudaMemcpy(enum unit starts)");
+    chk(cudaMalloc(&cx.d_blocks, g_enum_blocks.size() * sizeof(EnumBlockRec)), "cudaMalloc(enum blocks)");
+    chk(cudaMemcpy(cx.d_blocks, g_enum_blocks.data(), g_enum_blocks.size() * sizeof(EnumBlockRec), cudaMemcpyHostToDevice), "cudaMemcpy(enum blocks)");
     chk(cudaMalloc(&cx.d_counters, 2 * kCounterRing * sizeof(unsigned int)), "cudaMalloc(counters)");
     chk(cudaMemset(cx.d_counters, 0, 2 * kCounterRing * sizeof(unsigned int)), "cudaMemset(counters)");
     chk(cudaMalloc(&cx.d_h32, (size_t)kEnumRing * kHistBinsPad * sizeof(uint32_t)), "cudaMalloc(h32)");
@@ -1624,7 +1632,7 @@ static int launch_enum7(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin
     const uint64_t n_static = rounds * n_warps;
     k_enum7<<<(unsigned)ctas, kCtaThreads, kSmemEnum, st>>>(
         cx->d_enum, cx->d_trimask, reinterpret_cast<unsigned long long*>(hist9), reinterpret_cast<unsigned long long*>(hist7463), comb_begin, comb_end,
-        cx->d_units, cx->d_unit_starts, (uint32_t)unit_first, (uint32_t)n_units, (uint32_t)per_tile, (uint32_t)mine, (uint32_t)n_static, counter, h32, part, nparts, fa);
+        cx->d_units, cx->d_unit_starts, reinterpret_cast<const uint4*>(cx->d_blocks), (uint32_t)unit_first, (uint32_t)n_units, (uint32_t)per_tile, (uint32_t)mine, (uint32_t)n_static, counter, h32, part, nparts, fa);
     return after_launch("enum7 launch");
 }
 

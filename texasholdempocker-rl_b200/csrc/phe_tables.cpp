@@ -304,6 +304,23 @@ bool build_enum_image(unsigned char* image, uint64_t* trimask)
     return true;
 }
 
+void build_enum_blocks(std::vector<EnumBlockRec>& out)
+{
+    uint32_t binom[53 * 8];
+    build_binom(binom);
+    const Binom C{binom};
+    out.clear();
+    out.reserve(N_ENUM_BLOCKS);
+    for (int c6 = 6; c6 < 52; c6++)
+        for (int c5 = 5; c5 < c6; c5++)
+            for (int c4 = 4; c4 < c5; c4++)
+                for (int c3 = 3; c3 < c4; c3++) {
+                    EnumBlock b;
+                    enum_block_setup(c3, c4, c5, c6, C, b);
+                    out.push_back(EnumBlockRec{(uint32_t)b.s3, (uint32_t)(b.s3 >> 32), b.bidx3 | b.ntriples << 16, b.kbias});
+                }
+}
+
 void build_enum_units(std::vector<uint32_t>& out, std::vector<uint64_t>& starts, uint32_t max_hands, uint32_t max_blocks)
 {
     out.clear();
@@ -338,13 +355,13 @@ void build_enum_units(std::vector<uint32_t>& out, std::vector<uint64_t>& starts,
     starts.assign(out.size(), 0);
     size_t u = 0;
     uint32_t block_start = 0;
+    uint64_t block_id = 0;
     for (int c6 = 6; c6 < 52; c6++)
         for (int c5 = 5; c5 < c6; c5++)
             for (int c4 = 4; c4 < c5; c4++)
-                for (int c3 = 3; c3 < c4; c3++) {
+                for (int c3 = 3; c3 < c4; c3++, block_id++) {
                     const uint32_t block_end = block_start + binom_u32(c3, 3);
-                    for (; u + 1 < out.size() && out[u] < block_end; u++)
-                        starts[u] = (uint64_t)c3 | (uint64_t)c4 << 6 | (uint64_t)c5 << 12 | (uint64_t)c6 << 18 | (uint64_t)(out[u] - block_start) << 24;
+                    for (; u + 1 < out.size() && out[u] < block_end; u++) starts[u] = block_id | (uint64_t)(out[u] - block_start) << 18;
                     block_start = block_end;
                 }
 }

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "phe_core.cuh"
+#include "phe_enum.cuh"
 
 namespace phe {
 
@@ -28,11 +29,14 @@ void build_dealtab(uint64_t out[DEALTAB_ENTRIES]);
 // fills image[ENUM_IMG_BYTES] and trimask[N_TRIPLES] (layouts in phe_enum.cuh)
 bool build_enum_image(unsigned char* image, uint64_t* trimask);
 
+// records of all N_ENUM_BLOCKS enumeration blocks in colex order (phe_enum.cuh)
+void build_enum_blocks(std::vector<EnumBlockRec>& out);
+
 // Work units of the exhaustive enumeration on the colex axis of C(52,7): unit u covers [out[u], out[u+1]).  A unit ends
 // after `max_hands` hands or after `max_blocks` enumeration blocks (a block = one suffix (c3..c6), C(c3,3) hands), whichever
 // comes first -- runs of tiny blocks (wherever c4 restarts) cost a warp a serial set-up each, so they are cut by count.
 // out.front() == 0, out.back() == C(52,7).  starts[u] packs where unit u begins, so that the kernel need not unrank the index:
-// c3 | c4 << 6 | c5 << 12 | c6 << 18 | t << 24 with t = C(c2,3) + C(c1,2) + c0 the colex index of the triple inside its block
+// block id | t << 18 with t = C(c2,3) + C(c1,2) + c0 the colex index of the triple inside its block
 // (starts.size() == out.size(); the entry of the end sentinel is 0).
 void build_enum_units(std::vector<uint32_t>& out, std::vector<uint64_t>& starts, uint32_t max_hands, uint32_t max_blocks);
 
