@@ -265,10 +265,13 @@ __device__ __forceinline__ uint32_t enum_flush_addr(uint32_t x, uint32_t t, uint
                                                     const uint64_t* __restrict__ g_trimask)
 {
     const uint2 m = __ldg(reinterpret_cast<const uint2*>(g_trimask) + t);
-    const uint32_t s = (31u - (uint32_t)__clz(x)) >> 2;          // suit 0..3 from the flagged nibble
-    const uint32_t sel = s * 0x22u + 0x10u;                      // PRMT selector: bytes 2s and 2s+1 of {hi:lo}
-    const uint32_t suit_lane = __byte_perm(s3lo | m.x, s3hi | m.y, sel) & 0x1FFFu;
-    return a_fl + 2u * suit_lane;
+    uint32_t pos;                                                // bit 3, 7, 11 or 15: the flagged nibble (bfind = FLO, no 31 - clz round trip)
+    asm("bfind.u32 %0, %1;" : "=r"(pos) : "r"(x));
+    const uint32_t sel = (pos >> 2) * 0x22u + 0x10u;             // PRMT selector: bytes 2s and 2s+1 of {hi:lo}, s = suit 0..3
+    uint32_t two_lanes, addr;                                    // prmt directly: __byte_perm also masks the selector
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(two_lanes) : "r"(s3lo | m.x), "r"(s3hi | m.y), "r"(sel));
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr) : "r"(two_lanes & 0x1FFFu), "r"(a_fl));
+    return addr;
 }
 
 // ---- fused all-reduce epilogue (phe_enum7_allreduce) --------------------------------------------------------
