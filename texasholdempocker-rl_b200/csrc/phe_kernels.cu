@@ -569,9 +569,22 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
                     any |= x[u];
                 }
                 if (__any_sync(0xFFFFFFFFu, any != 0u)) {   // some lane holds a flush (3 % of hands)
+                    // two phases: first every flagged hand requests its triple's card set, then the addresses are formed -- the L2
+                    // round trips of the trip's flush hands overlap instead of queueing behind each other inside four separate
+                    // branch regions (long-scoreboard was the top stall; +1.5 % measured)
+                    uint2 tri_set[kU];
+#pragma unroll
+                    for (int u = 0; u < kU; u++) {
+                        tri_set[u] = make_uint2(0u, 0u);
+                        if (x[u]) tri_set[u] = __ldg(reinterpret_cast<const uint2*>(g_trimask) + (t0 + 32u * u));
+                    }
 #pragma unroll
                     for (int u = 0; u < kU; u++)
-                        if (x[u]) a[u] = enum_flush_addr(x[u], t0 + 32u * u, s3lo, s3hi, a_fl, g_trimask);
+                        if (x[u]) {
+                            const uint32_t w = x[u] > 0xFFu ? (s3hi | tri_set[u].y) : (s3lo | tri_set[u].x);   // suits 2, 3 live in the high word
+                            const uint32_t lane13 = ((x[u] & 0x8080u) ? w >> 16 : w) & 0x1FFFu;               // odd suits in the high half-word
+                            a[u] = a_fl + 2u * lane13;
+                        }
                 }
                 uint32_t r[kU];
 #pragma unroll
