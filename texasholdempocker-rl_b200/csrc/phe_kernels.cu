@@ -506,7 +506,7 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
     bool dynamic = false;
     for (;; j += n_warps) {
         if (!dynamic && j >= n_static) dynamic = true;
-        if (dynamic) {
+        if (dynamic) {   // (claiming one tile ahead hides the round trip but reserves a tile behind a busy warp: the finish line got 1-2 us worse)
             uint32_t got = 0;
             if (lane == 0) got = atomicAdd(tile_counter, 1u);
             j = n_static + __shfl_sync(0xFFFFFFFFu, got, 0);
@@ -1622,7 +1622,7 @@ static int launch_enum7(uint64_t* hist9, uint64_t* hist7463, uint64_t comb_begin
 #ifndef PHE_ENUM_TILES_PER_WARP
 #define PHE_ENUM_TILES_PER_WARP 8
 #endif
-    uint64_t per_tile = total / ((uint64_t)nparts * cx->sm_count * (kCtaThreads / 32) * PHE_ENUM_TILES_PER_WARP) / kEnumUnitHands;
+    uint64_t per_tile = (total / ((uint64_t)nparts * cx->sm_count * (kCtaThreads / 32) * PHE_ENUM_TILES_PER_WARP) + kEnumUnitHands / 2) / kEnumUnitHands;   // rounded
     if (per_tile < 1) per_tile = 1;
 #ifndef PHE_ENUM_TILE_UNITS
 #define PHE_ENUM_TILE_UNITS 4

@@ -41,5 +41,5 @@ for n in (10_000, 1_000_000, T // 8, T // 2, T):
           f"all summed +{(st[6]-t0)/1e3:.1f}  end +{(st[4]-t0)/1e3:.1f} us")
 hist = torch.zeros(7472, dtype=torch.int64, device="cuda")
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-for nparts in (1, 2, 8):
+for nparts in (1, 2, 4, 8):
     show(f"plain part 0 of {nparts}", lambda: L.phe_enum7_part(C.c_void_p(hist.data_ptr()), C.c_void_p(hist.data_ptr() + 72), 0, T, 0, nparts, st))
