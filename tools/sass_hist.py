@@ -2,9 +2,11 @@
 
   python tools/sass_hist.py [profiles/sass_rNN.txt]
 
-What to read in it: UBLKCP + SYNCS (TMA bulk copy + mbarrier) in the table-staging kernels, ATOMS.POPC.INC / REDUX in the
-enumeration, HMMA (legacy mma.sync) in k_attention, no UTC*MMA / LDTM anywhere: the hot path is integer / shared-memory
-lookup work that does not use tensor cores (north_star), so tcgen05 would only appear in the attention kernel."""
+What to read in it: UBLKCP + SYNCS (TMA bulk copy + mbarrier) in the table-staging kernels; ATOMS.POPC.INC / REDUX and
+UBLKRED (TMA bulk reduction of the histogram, cp.reduce.async.bulk) in the enumeration, whose multimem.red / multimem.st show
+up as REDG / STG .STRONG.SYS (the multicast is in the address mapping); UTCHMMA / LDTM / STTM / UTMALDG (tcgen05 + TMEM + TMA
+tensor loads) in k_attention_tc only: the hot path itself is integer / shared-memory lookup work that does not use tensor
+cores (north_star)."""
 import collections
 import importlib
 import os
@@ -23,7 +25,7 @@ def flush():
     if name:
         n = sum(hist.values())
         top = ", ".join(f"{k} {v}" for k, v in hist.most_common(18))
-        flags = [k for k in hist if k.startswith(("UBLKCP", "SYNCS", "ATOMS", "REDUX", "HMMA", "UTC", "LDTM", "UTMA", "RED", "ATOMG", "LDGSTS"))]
+        flags = [k for k in hist if k.startswith(("UBLKCP", "UBLKRED", "SYNCS", "STTM", "ATOMS", "REDUX", "HMMA", "UTC", "LDTM", "UTMA", "RED", "ATOMG", "LDGSTS"))]
         out.append(f"{name}\n  {n} instructions; notable: {', '.join(sorted(flags)) or '-'}\n  {top}\n")
 
 
