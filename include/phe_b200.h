@@ -79,10 +79,11 @@ int phe_eval7_host(const void *hands, int layout, int64_t n, uint16_t *ranks_out
  * may be NULL.  Shards of the index range may be summed in any order. */
 int phe_enum7(uint64_t *hist9, uint64_t *hist7463, uint64_t comb_begin, uint64_t comb_end, void *stream);
 int phe_enum7_host(uint64_t *hist9, uint64_t *hist7463, uint64_t comb_begin, uint64_t comb_end);
-/* Same range, but only part `part` of `nparts` interleaved parts: the range is cut into fixed tiles and tile t
- * belongs to part t % nparts.  Low colex indices are the expensive ones (short blocks), so interleaved parts
- * cost the same while contiguous halves do not; the parts' histograms add up to phe_enum7's exactly.  This is
- * how the range is sharded over GPUs. */
+/* Same range, but only part `part` of `nparts` interleaved parts: the range is cut into tiles (1-4 work units of at
+ * most 512 hands and 4 enumeration blocks each, a static table of the colex axis) and tile t belongs to part
+ * t % nparts.  Cost per hand varies along the axis (runs of short blocks), so interleaved parts cost the same while
+ * contiguous halves do not; the parts' histograms add up to phe_enum7's exactly.  This is how the range is sharded
+ * over GPUs. */
 int phe_enum7_part(uint64_t *hist9, uint64_t *hist7463, uint64_t comb_begin, uint64_t comb_end,
                    uint32_t part, uint32_t nparts, void *stream);
 

@@ -382,6 +382,25 @@ def test_enum7_fused_allreduce_single_rank(phe, oracle, torch):
     assert fe.check() == 8          # launches completed (3 + 1 eager, 4 replays; the capture itself launches nothing); no exchange timed out
 
 
+@pytest.mark.parametrize("nvls", ["0", "1"])
+def test_enum7_fused_allreduce_two_ranks(torch, nvls):
+    """The fused exchange between real peers (peer stores and NVLS multimem): tools/fused_enum_bench.py asserts the golden
+    histograms on every rank for eager launches, a sub-range and graph replays.  Needs two GPUs on the box."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PHE_FUSED_NVLS=nvls)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(29870 + int(nvls)), os.path.join(root, "tools", "fused_enum_bench.py")],
+                       capture_output=True, text=True, timeout=300, env=env, cwd=root)
+    if nvls == "1" and "no multicast mapping" in (r.stdout + r.stderr):
+        pytest.skip("no NVLS multicast mapping on this system")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert ("NVLS multimem" if nvls == "1" else "peer stores") in r.stdout
+
+
 def test_concurrent_callers(phe, oracle, torch):
     """Many Python threads in one process (the reference runs its game loops as threads, env/workflow.py:848-878):
     ctypes drops the GIL around every call, the library keeps per-thread scratch and no mutable global state."""
