@@ -244,18 +244,45 @@ PHE_HD int category_of(uint32_t rank)
 }
 
 // ---- Philox4x32-10 ---------------------------------------------------------------------------
-PHE_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
-                          uint32_t out[4])
+// The key of round r is (k0 + r * 0x9E3779B9, k1 + r * 0xBB67AE85).  The key is the seed, a launch constant, so the hot
+// kernels take the twenty round keys as a kernel parameter (RoundKeys: constant-bank operands of the XORs) instead of
+// re-deriving them with 18 additions in every block; SeedKey derives them on the fly (host code, cold kernels).
+struct SeedKey {
+    uint32_t lo, hi;
+    PHE_HD uint32_t k0(int r) const { return lo + (uint32_t)r * 0x9E3779B9u; }
+    PHE_HD uint32_t k1(int r) const { return hi + (uint32_t)r * 0xBB67AE85u; }
+};
+struct RoundKeys {
+    uint32_t k[20];
+    PHE_HD uint32_t k0(int r) const { return k[2 * r]; }
+    PHE_HD uint32_t k1(int r) const { return k[2 * r + 1]; }
+};
+PHE_HD SeedKey seed_key(uint64_t seed) { return SeedKey{(uint32_t)seed, (uint32_t)(seed >> 32)}; }
+inline RoundKeys round_keys(uint64_t seed)
+{
+    RoundKeys rk;
+    const SeedKey sk = seed_key(seed);
+    for (int r = 0; r < 10; r++) { rk.k[2 * r] = sk.k0(r); rk.k[2 * r + 1] = sk.k1(r); }
+    return rk;
+}
+
+template <class Key>
+PHE_HD void philox4x32_10_k(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const Key& key, uint32_t out[4])
 {
 PHE_UNROLL
     for (int r = 0; r < 10; r++) {
         const uint32_t h0 = umulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
         const uint32_t h1 = umulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-        c0 = h1 ^ c1 ^ k0; c1 = l1;
-        c2 = h0 ^ c3 ^ k1; c3 = l0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        c0 = h1 ^ c1 ^ key.k0(r); c1 = l1;
+        c2 = h0 ^ c3 ^ key.k1(r); c3 = l0;
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+PHE_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                          uint32_t out[4])
+{
+    philox4x32_10_k(c0, c1, c2, c3, SeedKey{k0, k1}, out);
 }
 
 // ---- dealing -----------------------------------------------------------------------------------
@@ -308,14 +335,14 @@ struct LocalSlots {             // host / small kernels: accepted slots kept in 
 };
 
 // returns the number of pair slots accepted (== n_pairs unless the input was malformed)
-template <class DealTab, class Slots>
-PHE_HD int deal_slots(const DealTab& dt, uint64_t known, uint64_t seed, uint64_t sample, uint32_t stream, bool want_single, int n_pairs,
-                      Slots& out, uint32_t one = 1u)
+template <class DealTab, class Slots, class Key>
+PHE_HD int deal_slots_k(const DealTab& dt, uint64_t known, const Key& key, uint64_t sample, uint32_t stream, bool want_single, int n_pairs,
+                        Slots& out, uint32_t one = 1u)
 {
     uint32_t used_lo = (uint32_t)known, used_hi = (uint32_t)(known >> 32);
-    const uint32_t s_lo = (uint32_t)sample, s_hi = (uint32_t)(sample >> 32), k_lo = (uint32_t)seed, k_hi = (uint32_t)(seed >> 32);
+    const uint32_t s_lo = (uint32_t)sample, s_hi = (uint32_t)(sample >> 32);
     uint32_t rnd[4];
-    philox4x32_10(s_lo, s_hi, stream, 0u, k_lo, k_hi, rnd);
+    philox4x32_10_k(s_lo, s_hi, stream, 0u, key, rnd);
     if (want_single) {
         bool have = false;
 PHE_UNROLL
@@ -328,7 +355,7 @@ PHE_UNROLL
         }
         for (uint32_t t = 0; !have && t < 64u; t++) {      // rare overflow path
             uint32_t ex[4];
-            philox4x32_10(s_lo, s_hi, stream, 0x80000000u + t, k_lo, k_hi, ex);
+            philox4x32_10_k(s_lo, s_hi, stream, 0x80000000u + t, key, ex);
             for (int d = 0; d < 8 && !have; d++) {
                 const uint32_t r = (ex[d >> 1] >> (16 * (d & 1))) & 0xFFFFu;
                 const uint64_t m = dt.mask(N_PAIRS + mod52_u16(r));
@@ -348,7 +375,7 @@ PHE_UNROLL
     int first_word = want_single ? 1 : 0;
     // 64 blocks = 512 draws: never reached with a valid state; bounds the loop on garbage
     for (uint32_t blk = 0; cur < end && blk < 64u; blk++) {
-        if (blk) philox4x32_10(s_lo, s_hi, stream, blk, k_lo, k_hi, rnd);
+        if (blk) philox4x32_10_k(s_lo, s_hi, stream, blk, key, rnd);
 PHE_UNROLL
         for (int wi = 0; wi < 4; wi++) {
             if (wi < first_word) continue;
@@ -373,14 +400,21 @@ PHE_UNROLL
     return got < n_pairs ? got : n_pairs;
 }
 
+template <class DealTab, class Slots>
+PHE_HD int deal_slots(const DealTab& dt, uint64_t known, uint64_t seed, uint64_t sample, uint32_t stream, bool want_single, int n_pairs,
+                      Slots& out, uint32_t one = 1u)
+{
+    return deal_slots_k(dt, known, seed_key(seed), sample, stream, want_single, n_pairs, out, one);
+}
+
 // one Monte-Carlo rollout (env/workflow.py:130-148 generalised to n_opp opponents):
 // returns 0 win, 1 tie, 2 loss for the hero.  `slots` is the scratch for the accepted deal slots.
-template <class Tab, class DealTab, class Slots>
-PHE_HD int mc_rollout(const Tab& tab, const HashParams& hp, const DealTab& dt, uint64_t known, uint64_t hero, int nboard, int n_opp,
-                      uint64_t seed, uint64_t sample, uint32_t stream, Slots& slots)
+template <class Tab, class DealTab, class Slots, class Key>
+PHE_HD int mc_rollout_k(const Tab& tab, const HashParams& hp, const DealTab& dt, uint64_t known, uint64_t hero, int nboard, int n_opp,
+                        const Key& key, uint64_t sample, uint32_t stream, Slots& slots)
 {
     const int nbm = 5 - nboard, nbp = nbm >> 1;
-    deal_slots(dt, known, seed, sample, stream, (nbm & 1) != 0, nbp + n_opp, slots, hp.one);
+    deal_slots_k(dt, known, key, sample, stream, (nbm & 1) != 0, nbp + n_opp, slots, hp.one);
     uint64_t board = known & ~hero;
     if (nbm & 1) board |= slots.get_single();
     for (int k = 0; k < nbp; k++) board |= slots.get_pair(k, dt);
@@ -402,6 +436,13 @@ PHE_HD int mc_rollout(const Tab& tab, const HashParams& hp, const DealTab& dt, u
     }
 #endif
     return hr < best ? 0 : (hr == best ? 1 : 2);
+}
+
+template <class Tab, class DealTab, class Slots>
+PHE_HD int mc_rollout(const Tab& tab, const HashParams& hp, const DealTab& dt, uint64_t known, uint64_t hero, int nboard, int n_opp,
+                      uint64_t seed, uint64_t sample, uint32_t stream, Slots& slots)
+{
+    return mc_rollout_k(tab, hp, dt, known, hero, nboard, n_opp, seed_key(seed), sample, stream, slots);
 }
 
 // `need` cards as ids, for phe_deal and the random step of equity plans.  Slot order = single (if need is odd), then

@@ -710,9 +710,9 @@ struct SmemSlots {
 // K3: Monte-Carlo equity.  One warp works on one (state, sample chunk) item at a time; lanes take
 // samples chunk_begin + lane + 32 i.  The deal is a pure function of the global sample index.
 // ------------------------------------------------------------------------------------------------
-template <class Tab, class DealTab>
+template <class Tab, class DealTab, class Key>
 __device__ __forceinline__ void equity_mc_body(const Tab& tab, const DealTab& dt, const ulonglong2* __restrict__ states, int64_t n_states,
-                                               int n_opp_default, uint64_t rollouts, uint64_t sample_offset, uint64_t seed,
+                                               int n_opp_default, uint64_t rollouts, uint64_t sample_offset, const Key& key,
                                                uint32_t state_base, unsigned long long* __restrict__ wtl, uint32_t chunk,
                                                SmemSlots slots, unsigned int* __restrict__ item_counter)
 {
@@ -746,7 +746,7 @@ __device__ __forceinline__ void equity_mc_body(const Tab& tab, const DealTab& dt
         if (e > rollouts) e = rollouts;
         uint32_t w = 0, t = 0, l = 0;
         for (uint64_t i = b + lane; i < e; i += 32) {
-            const int res = mc_rollout(tab, hp, dt, known, hero, nboard, n_opp, seed, sample_offset + i, state_base + (uint32_t)s, slots);
+            const int res = mc_rollout_k(tab, hp, dt, known, hero, nboard, n_opp, key, sample_offset + i, state_base + (uint32_t)s, slots);
             w += (res == 0); t += (res == 1); l += (res == 2);
         }
         w = __reduce_add_sync(0xFFFFFFFFu, w);
@@ -762,7 +762,7 @@ __device__ __forceinline__ void equity_mc_body(const Tab& tab, const DealTab& dt
 
 __global__ void __launch_bounds__(kMcThreads, 1) PHE_MC_CLUSTER_ATTR
 k_equity_mc_smem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict__ g_dealtab, const ulonglong2* __restrict__ states,
-                 int64_t n_states, int n_opp, uint64_t rollouts, uint64_t sample_offset, uint64_t seed, uint32_t state_base,
+                 int64_t n_states, int n_opp, uint64_t rollouts, uint64_t sample_offset, const RoundKeys rkeys, uint32_t state_base,
                  unsigned long long* __restrict__ wtl, uint32_t chunk, unsigned int* __restrict__ counters)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -779,7 +779,7 @@ k_equity_mc_smem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
     const SharedTab tab{sb};
     const SharedDealTab dt{sb + kSmemTabOnly};
     const SmemSlots slots{sb + kSmemTabOnly + kDealTabBytes + 4u * threadIdx.x, 4u * blockDim.x, 0ull};
-    equity_mc_body(tab, dt, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk, slots, counters);
+    equity_mc_body(tab, dt, states, n_states, n_opp, rollouts, sample_offset, rkeys, state_base, wtl, chunk, slots, counters);
     // completion ticket: the last CTA re-arms the {item counter, ticket} pair for the next launch that draws it
     __shared__ uint32_t s_last;
     __syncthreads();
@@ -1053,7 +1053,7 @@ k_equity_mc_gmem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
     const GlobalTab tab{g_tab};
     const GlobalDealTab dt{g_dealtab};
     const SmemSlots slots{(uint32_t)__cvta_generic_to_shared(s_slots) + 4u * threadIdx.x, 4u * blockDim.x, 0ull};
-    equity_mc_body(tab, dt, states, n_states, n_opp, rollouts, sample_offset, seed, state_base, wtl, chunk, slots, nullptr);
+    equity_mc_body(tab, dt, states, n_states, n_opp, rollouts, sample_offset, seed_key(seed), state_base, wtl, chunk, slots, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1768,7 +1768,7 @@ int phe_equity_mc(const uint64_t* states, int64_t n_states, int n_opp, uint64_t 
 #ifdef PHE_MC_POOL
         k_equity_mc_pool<<<(unsigned)ctas, kCtaThreads, kSmemMcPool, st>>>(cx->d_image, cx->d_pairmask, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk, counters);
 #else
-        k_equity_mc_smem<<<(unsigned)ctas, kMcThreads, kSmemMc, st>>>(cx->d_image, cx->d_pairmask, sp, n_states, n_opp, rollouts, sample_offset, seed, state_index_base, wp, (uint32_t)chunk, counters);
+        k_equity_mc_smem<<<(unsigned)ctas, kMcThreads, kSmemMc, st>>>(cx->d_image, cx->d_pairmask, sp, n_states, n_opp, rollouts, sample_offset, round_keys(seed), state_index_base, wp, (uint32_t)chunk, counters);
 #endif
     }
     return after_launch("equity_mc launch");
