@@ -675,10 +675,12 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
 // words of one row: conflict free; 32-bit cells avoid the 16-bit conversions around the store); the single card set stays in a register.
 struct SharedDealTab {
     uint32_t base;
+    uint32_t eight;    // 8, derived from the opaque c_hp.two: the entry address is q * eight + base, an IMAD on the FMA pipe
+                       // (the alu pipe bounds the kernel and a visible 8 becomes an LEA there: 23 of them per warp-rollout)
     __device__ __forceinline__ uint64_t mask(uint32_t q) const
     {
         uint64_t v;
-        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(base + 8u * q));
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(q * eight + base));
         return v;
     }
 };
@@ -777,7 +779,7 @@ k_equity_mc_smem(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
     sb += (uint32_t)(rollouts >> 63);
 #endif
     const SharedTab tab{sb};
-    const SharedDealTab dt{sb + kSmemTabOnly};
+    const SharedDealTab dt{sb + kSmemTabOnly, c_hp.two * c_hp.two * c_hp.two};
     const SmemSlots slots{sb + kSmemTabOnly + kDealTabBytes + 4u * threadIdx.x, 4u * blockDim.x, 0ull};
     equity_mc_body(tab, dt, states, n_states, n_opp, rollouts, sample_offset, rkeys, state_base, wtl, chunk, slots, counters);
     // completion ticket: the last CTA re-arms the {item counter, ticket} pair for the next launch that draws it
@@ -857,7 +859,7 @@ k_equity_mc_pool(const uint16_t* __restrict__ g_tab, const uint64_t* __restrict_
     __syncthreads();
     const HashParams hp = c_hp;
     const SharedTab tab{sb};
-    const SharedDealTab dt{sb + kSmemTabOnly};
+    const SharedDealTab dt{sb + kSmemTabOnly, c_hp.two * c_hp.two * c_hp.two};
     const uint32_t k_lo = (uint32_t)seed, k_hi = (uint32_t)(seed >> 32);
     uint32_t col = lane;
     uint32_t rf = 0, rr = 32, rt = 32;       // ring cursors: free [rf, rr), ready [rr, rt)  (mod 64)
