@@ -81,10 +81,24 @@ PHE_HD uint32_t or_disjoint(uint32_t a, uint32_t b, uint32_t one)
 #endif
 }
 
+// the same for the two ORs of board | hole cards in front of every evaluation: these are NOT on the dealing loop's dependent
+// chain, so the FMA form was judged on its own (-DPHE_FMA_EVAL_OR): 3.990e10 against 4.023e10 rollouts/s, and the cursor add
+// alone (-DPHE_FMA_CURSOR) 3.942e10 -- a multiply by a register-held 1 is not a free way off the logic pipe; only the table
+// ADDRESSES (idx * two + base, q * eight + base), where the multiply replaces a shift-add, pay.  Both stay off.
+PHE_HD uint32_t or_disjoint_eval(uint32_t a, uint32_t b, uint32_t one)
+{
+#if defined(__CUDA_ARCH__) && (defined(PHE_PIPE_BALANCE) || defined(PHE_FMA_EVAL_OR))
+    return b * one + a;
+#else
+    (void)one;
+    return a | b;
+#endif
+}
+
 // a + b as b * one + a: the same trick for a plain addition (cursor bookkeeping of the dealing loop)
 PHE_HD uint32_t add_fma(uint32_t a, uint32_t b, uint32_t one)
 {
-#if defined(__CUDA_ARCH__) && defined(PHE_PIPE_BALANCE)
+#if defined(__CUDA_ARCH__) && (defined(PHE_PIPE_BALANCE) || defined(PHE_FMA_CURSOR))
     return b * one + a;
 #else
     (void)one;
@@ -231,7 +245,7 @@ template <class Tab>
 PHE_HD uint32_t eval7_board(uint32_t blo, uint32_t bhi, const BoardFlush& bf, uint64_t hole, const Tab& tab, const HashParams& hp)
 {
     const uint32_t plo = (uint32_t)hole, phi = (uint32_t)(hole >> 32);
-    const uint32_t inf = noflush_slot(or_disjoint(blo, plo, hp.one), or_disjoint(bhi, phi, hp.one), tab, hp);
+    const uint32_t inf = noflush_slot(or_disjoint_eval(blo, plo, hp.one), or_disjoint_eval(bhi, phi, hp.one), tab, hp);
     const uint32_t lane = (((bf.hi ? phi : plo) >> bf.sh) & bf.pm) | bf.lane;
     return tab.ld_rank(popc32(lane) >= 5, lane, inf, hp);
 }
