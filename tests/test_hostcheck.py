@@ -125,6 +125,22 @@ def test_enum_block_walk_full(hostcheck):
     assert h.tolist() == json.load(open(os.path.join(GOLDEN, "hist7463.json")))["hist7463"]
 
 
+def test_philox_round_keys(hostcheck, oracle):
+    """phe_core.cuh: Philox with precomputed round keys (the MC kernel's launch parameter) == Philox with the seed as key ==
+    the oracle's, on the Random123 vectors and on random counters / seeds."""
+    hostcheck.hc_philox.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    hostcheck.hc_philox.restype = None
+    rng = np.random.default_rng(7)
+    cases = [([0] * 4, 0), ([0xffffffff] * 4, 0xffffffffffffffff), ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], 0x299f31d0a4093822)]
+    cases += [(rng.integers(0, 2**32, 4).tolist(), int(rng.integers(0, 2**63)) * 2 + int(rng.integers(0, 2))) for _ in range(200)]
+    for ctr, seed in cases:
+        c = np.array(ctr, dtype=np.uint32)
+        out = np.zeros(8, dtype=np.uint32)
+        hostcheck.hc_philox(vp(c), seed, vp(out))
+        want = oracle.philox4x32_10(ctr, [seed & 0xffffffff, seed >> 32]).tolist()
+        assert out[:4].tolist() == want and out[4:].tolist() == want
+
+
 def test_enum_work_units(hostcheck):
     """build_enum_units (phe_tables.cpp): the enumeration kernel's tiles.  Units partition [0, C(52,7)), hold at most 512 hands
     and at most 4 whole enumeration blocks (a block = one (c3..c6) suffix = C(c3,3) consecutive colex indices)."""

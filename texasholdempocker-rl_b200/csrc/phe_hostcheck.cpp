@@ -138,6 +138,15 @@ void hc_settle(uint64_t board, const uint64_t* holes, int P, int R, int button, 
     settle_game(P, R, button, small_blind, onboard, ranks, act, val, won, result, card, paid);
 }
 
+// the product's Philox with the key derived on the fly (SeedKey) and with the twenty round keys precomputed (RoundKeys: what
+// the Monte-Carlo kernel takes as a launch parameter); out[0..4) and out[4..8) must agree with each other and with the oracle
+void hc_philox(const uint32_t ctr[4], uint64_t seed, uint32_t out[8])
+{
+    philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], (uint32_t)seed, (uint32_t)(seed >> 32), out);
+    const RoundKeys rk = round_keys(seed);
+    philox4x32_10_k(ctr[0], ctr[1], ctr[2], ctr[3], rk, out + 4);
+}
+
 // work-unit boundaries of the enumeration kernel (build_enum_units); returns the count, copies at most `cap` entries
 int64_t hc_enum_units(uint32_t max_hands, uint32_t max_blocks, uint32_t* out, uint64_t* starts_out, int64_t cap)
 {
