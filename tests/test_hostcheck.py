@@ -145,24 +145,28 @@ def test_enum_work_units(hostcheck):
     """build_enum_units (phe_tables.cpp): the enumeration kernel's tiles.  Units partition [0, C(52,7)), hold at most 512 hands
     and at most 4 whole enumeration blocks (a block = one (c3..c6) suffix = C(c3,3) consecutive colex indices)."""
     from math import comb
-    hostcheck.hc_enum_units.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int64]
+    hostcheck.hc_enum_units.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int64]
     hostcheck.hc_enum_units.restype = C.c_int64
     buf = np.zeros(400000, dtype=np.uint32)
     starts = np.zeros(400000, dtype=np.uint64)
-    n = hostcheck.hc_enum_units(512, 4, vp(buf), vp(starts), len(buf))
+    n = hostcheck.hc_enum_units(512, 4, 128, vp(buf), vp(starts), len(buf))
     u = buf[:n].astype(np.int64)
     assert u[0] == 0 and u[-1] == 133784560 and (np.diff(u) > 0).all() and np.diff(u).max() <= 512
     sizes = np.array([comb(c3, 3) for c6 in range(6, 52) for c5 in range(5, c6) for c4 in range(4, c5) for c3 in range(3, c4)], dtype=np.int64)
     ends = np.cumsum(sizes)                                            # block ends on the colex axis
     starts_in = np.searchsorted(ends, u[1:], side="right") - np.searchsorted(ends, u[:-1], side="right")   # block ends inside each unit
     assert starts_in.max() <= 4
-    assert n < 300000                                                  # ~1.1 MB + 2.2 MB tables
+    assert n < 340000                                                  # ~1.3 MB + 2.6 MB tables
     # the packed start of every unit is the colex unranking of its first index
     st = starts[:n - 1].astype(np.int64)
     blk, tri = st & ((1 << 18) - 1), st >> 18
     block_start = np.concatenate([[0], ends[:-1]])                     # block id = position in colex order of the (c3..c6) suffixes
     assert blk.max() == len(sizes) - 1 == 211876 - 1 and (np.diff(blk) >= 0).all()
     assert (tri < sizes[blk]).all() and (block_start[blk] + tri == u[:-1]).all()
+    # a unit that resumes a block it did not begin starts on a whole 128-hand trip of that block, unless the previous unit was
+    # too short to reach one (then the cut could not advance)
+    resumed = tri > 0
+    assert (tri[resumed] % 128 == 0).mean() > 0.99
 
 
 def test_multiply_shift_reductions_are_exact():

@@ -148,11 +148,11 @@ void hc_philox(const uint32_t ctr[4], uint64_t seed, uint32_t out[8])
 }
 
 // work-unit boundaries of the enumeration kernel (build_enum_units); returns the count, copies at most `cap` entries
-int64_t hc_enum_units(uint32_t max_hands, uint32_t max_blocks, uint32_t* out, uint64_t* starts_out, int64_t cap)
+int64_t hc_enum_units(uint32_t max_hands, uint32_t max_blocks, uint32_t align, uint32_t* out, uint64_t* starts_out, int64_t cap)
 {
     std::vector<uint32_t> u;
     std::vector<uint64_t> st;
-    build_enum_units(u, st, max_hands, max_blocks);
+    build_enum_units(u, st, max_hands, max_blocks, align);
     for (int64_t i = 0; i < (int64_t)u.size() && i < cap; i++) {
         out[i] = u[(size_t)i];
         starts_out[i] = st[(size_t)i];

@@ -1369,7 +1369,10 @@ void init_device(int device)
         g_enum_image.resize(ENUM_IMG_BYTES);
         g_trimask.resize(N_TRIPLES);
         g_image_ok = g_image_ok && build_enum_image(g_enum_image.data(), g_trimask.data());
-        build_enum_units(g_enum_units, g_enum_unit_starts, kEnumUnitHands, kEnumUnitBlocks);
+#ifndef PHE_ENUM_UNIT_ALIGN
+#define PHE_ENUM_UNIT_ALIGN 128
+#endif
+        build_enum_units(g_enum_units, g_enum_unit_starts, kEnumUnitHands, kEnumUnitBlocks, PHE_ENUM_UNIT_ALIGN);
         build_enum_blocks(g_enum_blocks);
         build_binom(g_binom);
     });

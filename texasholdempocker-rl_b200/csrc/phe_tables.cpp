@@ -321,8 +321,9 @@ void build_enum_blocks(std::vector<EnumBlockRec>& out)
                 }
 }
 
-void build_enum_units(std::vector<uint32_t>& out, std::vector<uint64_t>& starts, uint32_t max_hands, uint32_t max_blocks)
+void build_enum_units(std::vector<uint32_t>& out, std::vector<uint64_t>& starts, uint32_t max_hands, uint32_t max_blocks, uint32_t align)
 {
+    if (align == 0) align = 1;
     out.clear();
     out.push_back(0);
     uint32_t unit_start = 0, blocks_in = 0, pos = 0;
@@ -331,9 +332,23 @@ void build_enum_units(std::vector<uint32_t>& out, std::vector<uint64_t>& starts,
             for (int c4 = 4; c4 < c5; c4++)
                 for (int c3 = 3; c3 < c4; c3++) {
                     const uint32_t block_end = pos + binom_u32(c3, 3);
+                    const uint32_t block_start = pos;
                     for (;;) {
-                        const uint32_t room = max_hands - (pos - unit_start);
+                        uint32_t room = max_hands - (pos - unit_start);
                         if (block_end - pos >= room) {            // the unit fills up inside (or exactly at the end of) this block
+                            // cut on a multiple of `align` hands from the block's start when that still advances: a tile that
+                            // resumes the block there starts on a whole trip of the kernel's 4 x 32-hand loop, and only the
+                            // block's last segment is left with a remainder of single trips
+                            const uint32_t off = pos + room - block_start, aligned = off - off % align;
+                            if (pos + room < block_end) {
+                                if (aligned > pos - block_start) room = block_start + aligned - pos;
+                                else if (pos > unit_start) {      // no aligned cut within reach: close the unit in front of the block
+                                    out.push_back(pos);
+                                    unit_start = pos;
+                                    blocks_in = 0;
+                                    continue;
+                                }
+                            }
                             pos += room;
                             out.push_back(pos);
                             unit_start = pos;

@@ -34,10 +34,10 @@ void build_enum_blocks(std::vector<EnumBlockRec>& out);
 
 // Work units of the exhaustive enumeration on the colex axis of C(52,7): unit u covers [out[u], out[u+1]).  A unit ends
 // after `max_hands` hands or after `max_blocks` enumeration blocks (a block = one suffix (c3..c6), C(c3,3) hands), whichever
-// comes first -- runs of tiny blocks (wherever c4 restarts) cost a warp a serial set-up each, so they are cut by count.
+// comes first (a cut inside a block falls on a multiple of `align` hands from the block's start) -- runs of tiny blocks (wherever c4 restarts) cost a warp a serial set-up each, so they are cut by count.
 // out.front() == 0, out.back() == C(52,7).  starts[u] packs where unit u begins, so that the kernel need not unrank the index:
 // block id | t << 18 with t = C(c2,3) + C(c1,2) + c0 the colex index of the triple inside its block
 // (starts.size() == out.size(); the entry of the end sentinel is 0).
-void build_enum_units(std::vector<uint32_t>& out, std::vector<uint64_t>& starts, uint32_t max_hands, uint32_t max_blocks);
+void build_enum_units(std::vector<uint32_t>& out, std::vector<uint64_t>& starts, uint32_t max_hands, uint32_t max_blocks, uint32_t align = 1);
 
 }  // namespace phe
