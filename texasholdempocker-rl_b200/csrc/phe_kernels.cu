@@ -539,7 +539,7 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
             t_start = C(c[2], 3) + C(c[1], 2) + (uint32_t)c[0];
         }
         if (wb >= we) continue;
-        uint64_t remaining = we - wb;
+        uint32_t remaining = (uint32_t)(we - wb);                    // a tile is at most 4 units = 2048 hands: 32-bit bookkeeping
         // block records come from the L2-resident table (one 16-byte load instead of eight binomial look-ups and the
         // suit arithmetic of enum_block_setup: block set-up was a fifth of all executed instructions); the next block's
         // record is requested before this block's hands are processed
@@ -547,7 +547,7 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
         for (;;) {
             const uint4 rec_next = __ldg(g_blocks + min(blk + 1u, N_ENUM_BLOCKS - 1u));
             uint32_t stop = rec.z >> 16;                              // ntriples
-            if ((uint64_t)stop > (uint64_t)t_start + remaining) stop = (uint32_t)(t_start + remaining);
+            stop = min(stop, t_start + remaining);                   // t_start < 17296, remaining <= 2048: no overflow
             const uint32_t msb = a_ms + 2u * (rec.z & 0xFFFFu);
             const uint32_t s3lo = rec.x, s3hi = rec.y, kbias = rec.w;
             // warp-uniform trip counts; kU hands per lane per trip keep kU independent LDS -> (LDG) -> LDS -> ATOMS
@@ -568,7 +568,7 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
                     x[u] = (e[u] + kbias) & 0x8888u;
                     any |= x[u];
                 }
-                if (__any_sync(0xFFFFFFFFu, any != 0u)) {   // some lane holds a flush (3 % of hands)
+                if (__any_sync(0xFFFFFFFFu, any != 0u)) {   // some lane holds a flush (3 % of hands; taken by 98 % of the trips, yet dropping the vote costs 7 %)
                     // two phases: first every flagged hand requests its triple's card set, then the addresses are formed -- the L2
                     // round trips of the trip's flush hands overlap instead of queueing behind each other inside four separate
                     // branch regions (long-scoreboard was the top stall; +1.5 % measured)
