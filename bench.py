@@ -506,12 +506,19 @@ def main():
 
     if not args.skip_extras and args.config == 3:
         # ---- config 2 as a side object at every N --------------------------------------------------------------------------
-        em, fused_keepalive = enum_measure(min(args.steps, 20))
-        extras["enum7"] = {"value": em["value"], "unit": "evals/s", "ms_per_step": em["ms_per_step"], "kernel_ms": em["kern_ms"], "e2e": em["e2e"],
-                           "config": {"workload": "exhaustive_c52_7 (BASELINE config 2)", "hands_per_step": NUM_HANDS, "collective": em["collective"]},
-                           "roofline": int_roofline("k_enum7", em["hands_this_rank"] / (em["kern_ms"] * 1e-3), "hand", em["kern_ms"], W_EVAL_LANE_OPS)}
+        # the side objects must never cost the headline line: a Python-level failure in one of them is reported in its place
+        try:
+            em, fused_keepalive = enum_measure(min(args.steps, 20))
+            extras["enum7"] = {"value": em["value"], "unit": "evals/s", "ms_per_step": em["ms_per_step"], "kernel_ms": em["kern_ms"], "e2e": em["e2e"],
+                               "config": {"workload": "exhaustive_c52_7 (BASELINE config 2)", "hands_per_step": NUM_HANDS, "collective": em["collective"]},
+                               "roofline": int_roofline("k_enum7", em["hands_this_rank"] / (em["kern_ms"] * 1e-3), "hand", em["kern_ms"], W_EVAL_LANE_OPS)}
+        except Exception as ex:  # noqa: BLE001
+            extras["enum7"] = {"error": f"{type(ex).__name__}: {ex}"}
         if rank == 0 and world == 1:
-            extras.update(single_gpu_extras(phe, torch, np, dev))
+            try:
+                extras.update(single_gpu_extras(phe, torch, np, dev))
+            except Exception as ex:  # noqa: BLE001
+                extras["single_gpu_extras_error"] = f"{type(ex).__name__}: {ex}"
         barrier()
     clocks = sampler.stop() if rank == 0 else None
 
