@@ -492,10 +492,10 @@ k_enum7(const unsigned char* __restrict__ g_img, const uint64_t* __restrict__ g_
     const uint32_t lane = threadIdx.x & 31;
     const Binom C{c_binom};
 
-    // Dynamic tile scheduling: a tile = `units_per_tile` consecutive work units of the colex axis (g_units: at most 512 hands
-    // or 4 enumeration blocks each, see build_enum_units), handed out through an atomic counter in increasing order.  Cutting
-    // by block count as well as by hands bounds the serial block set-ups one warp can be handed (runs of tiny blocks occur
-    // wherever c4 restarts), which is what kept single warps busy long after the rest of the launch had drained.
+    // Tiles: a tile = `units_per_tile` consecutive work units of the colex axis (g_units: at most 512 hands or 4 enumeration
+    // blocks each, see build_enum_units).  Cutting by block count as well as by hands bounds the serial block set-ups one warp
+    // can be handed (runs of tiny blocks occur wherever c4 restarts), which is what kept single warps busy long after the rest
+    // of the launch had drained.
     const uint32_t a_bin = sb + kEnumBinOff;
     // A launch owns the tiles == part (mod nparts); its j-th tile goes to warp j (mod W) for j < n_static (no atomic, W = warps
     // of the grid: up to six rounds), the rest through the counter.  One 4736-way contended counter for EVERY tile was the
